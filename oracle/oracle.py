@@ -80,6 +80,7 @@ def lib():
         L.orc_mesh_create.argtypes = [c_double_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_double]
         L.orc_mesh_free.argtypes = [C.c_void_p]
         L.orc_gravity.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, C.c_int]
+        L.orc_gravity_direct.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p]
         L.orc_rotate_point.argtypes = [C.c_double, c_double_p, c_double_p, C.c_double, c_double_p]
         L.orc_compute_motion.argtypes = [C.c_void_p, C.POINTER(OrcParams), C.c_double, c_double_p, c_double_p]
         L.orc_compute_trajectory.restype = C.c_int
@@ -210,6 +211,14 @@ def gravity(mesh: Mesh, pts, threads=1, potential=False):
     pot = np.empty(len(pts)) if potential else None
     lib().orc_gravity(mesh.handle, _dp(pts), len(pts), _dp(acc), _dp(pot) if potential else None, threads)
     return (acc, pot) if potential else acc
+
+
+def gravity_direct(mesh: Mesh, pts):
+    """Literal Tsoulis LN/AN transcription (cross-check of `gravity`)."""
+    pts = _f64(pts).reshape(-1, 3)
+    acc = np.empty_like(pts)
+    lib().orc_gravity_direct(mesh.handle, _dp(pts), len(pts), _dp(acc), None)
+    return acc
 
 
 def rotate_point(t, x, axis, w):

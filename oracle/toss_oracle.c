@@ -121,8 +121,9 @@ void orc_mesh_free(orc_mesh *m)
 
 int orc_mesh_faces(const orc_mesh *m) { return m->F; }
 
-/* polyhedral_gravity (Tsoulis 2012) -- SURVEY.md App. A.1.  Package sign convention. */
-static void gravity_point(const orc_mesh *m, const double P[3], double acc[3], double *pot)
+/* polyhedral_gravity (Tsoulis 2012) -- SURVEY.md App. A.1, transcribed term by term.  Package sign
+ * convention.  Kept as the cross-check of gravity_point() below (orc_gravity_direct). */
+static void gravity_point_direct(const orc_mesh *m, const double P[3], double acc[3], double *pot)
 {
     double ax = 0.0, ay = 0.0, az = 0.0, vv = 0.0;
     for (int f = 0; f < m->F; ++f) {
@@ -166,6 +167,56 @@ static void gravity_point(const orc_mesh *m, const double P[3], double acc[3], d
     acc[1] = m->Grho * ay;
     acc[2] = m->Grho * az;
     if (pot) *pot = 0.5 * m->Grho * vv;
+}
+
+
+/* Same Tsoulis sum S_p = sum_q hq_s LN_pq + hp (sum_q sigma_pq AN_pq + sing A_p), with the two
+ * transcendental arguments written in their cancellation-free closed forms:
+ *   LN_pq = ln((s2+l2)/(s1+l1)) = ln((l1+l2+|G|)/(l1+l2-|G|)) = 2 atanh(|G| / (l1+l2))
+ *   hp (sum_q sigma_pq AN_pq + sing A_p) = -hp_s * omega_p,
+ *   omega_p = 2 atan2(r0.(r1 x r2), l0 l1 l2 + l0 (r1.r2) + l1 (r2.r0) + l2 (r0.r1))   (signed solid angle)
+ * (Werner & Scheeres 1997 eqs. 7-10 / van Oosterom & Strackee 1983; identical values, see
+ * tests/test_oracle_gravity.py which checks both forms against a 50-digit mpmath evaluation.)
+ * The direct form loses ~ (l1+l2)/|G| ulps in ln(ratio ~ 1) and in the difference of two O(1)
+ * arctangents; this form keeps every term to a few ulp, so it is the one parity is anchored on. */
+static void gravity_point(const orc_mesh *m, const double P[3], double acc[3], double *pot)
+{
+    double ax = 0.0, ay = 0.0, az = 0.0, vv = 0.0;
+    for (int f = 0; f < m->F; ++f) {
+        const double *rc = m->rec + (size_t)f * REC;
+        const double *N = rc + 9;
+        double r[3][3], l[3];
+        for (int i = 0; i < 3; ++i) {
+            for (int c = 0; c < 3; ++c) r[i][c] = rc[3 * i + c] - P[c];
+            l[i] = norm3(r[i]);
+        }
+        double hp_s = dot3(N, r[0]);
+        double S = 0.0;
+        for (int q = 0; q < 3; ++q) {
+            const double *n = rc + 21 + 3 * q;
+            double hq_s = dot3(n, r[q]);
+            double z = rc[30 + q] / (l[q] + l[(q + 1) % 3]);
+            S += hq_s * (2.0 * atanh(z));
+        }
+        double c12[3];
+        cross3(r[1], r[2], c12);
+        double num = dot3(r[0], c12);
+        double den = l[0] * l[1] * l[2] + l[0] * dot3(r[1], r[2]) + l[1] * dot3(r[2], r[0]) + l[2] * dot3(r[0], r[1]);
+        S -= hp_s * (2.0 * atan2(num, den));
+        ax += N[0] * S;
+        ay += N[1] * S;
+        az += N[2] * S;
+        vv += hp_s * S;
+    }
+    acc[0] = m->Grho * ax;
+    acc[1] = m->Grho * ay;
+    acc[2] = m->Grho * az;
+    if (pot) *pot = 0.5 * m->Grho * vv;
+}
+
+void orc_gravity_direct(const orc_mesh *m, const double *pts, int64_t n, double *acc, double *pot)
+{
+    for (int64_t i = 0; i < n; ++i) gravity_point_direct(m, pts + 3 * i, acc + 3 * i, pot ? pot + i : NULL);
 }
 
 typedef struct {

@@ -8,7 +8,10 @@
  * rasmusmarak/TOSS).  Third-party arithmetic that is NOT in the reference tree
  * (polyhedral-gravity-model, desolver, pyquaternion; all un-pinned in
  * environment.yml:5-19) is restated from the published algorithms:
- *   - Tsoulis (2012) line-integral polyhedral gravity,
+ *   - Tsoulis (2012) line-integral polyhedral gravity, with the LN / AN
+ *     arguments in their cancellation-free closed forms (2 atanh(|G|/(l1+l2)); signed solid
+ *     angle by one atan2) -- same values, ~100x less rounding noise than the literal form,
+ *     which is kept as orc_gravity_direct and compared in tests/test_oracle_gravity.py,
  *   - Prince & Dormand (1981) RK8(7)-13M with desolver's step controller
  *     (safety 0.8, exponent 1/8, max-norm) and desolver's
  *     cubic-Hermite dense output,
@@ -66,6 +69,9 @@ int orc_mesh_faces(const orc_mesh *m);
 /* polyhedral_gravity.GravityEvaluable.__call__ (call site equations_of_motion.py:58):
  * acc is the PACKAGE sign convention (TOSS negates it, equations_of_motion.py:59). */
 void orc_gravity(const orc_mesh *m, const double *pts, int64_t n, double *acc, double *pot, int threads);
+/* the same sum with LN/AN transcribed literally from Tsoulis (2012); ~1e-12 relative rounding
+ * noise on the fine meshes (tests/test_oracle_gravity.py) -- cross-check only. */
+void orc_gravity_direct(const orc_mesh *m, const double *pts, int64_t n, double *acc, double *pot);
 
 /* equations_of_motion.py:98-117 */
 void orc_rotate_point(double t, const double x[3], const double axis[3], double w, double out[3]);
