@@ -1,0 +1,173 @@
+/* include/toss_b200.h -- C ABI of libtoss_b200.so: the B200 (sm_100a) population-fitness path of TOSS.
+ *
+ * This is the drop-in boundary.  The reference (rasmusmarak/TOSS) is pure
+ * Python; what its hot path binds today are three third-party packages, one call per RK stage:
+ *     polyhedral_gravity.GravityEvaluable.__call__      toss/trajectory/equations_of_motion.py:58
+ *     desolver.OdeSystem(...).integrate(events=...)     toss/trajectory/compute_trajectory.py:243-259
+ *     pyquaternion.Quaternion(axis, angle).rotate       toss/trajectory/equations_of_motion.py:112-115
+ * and numpy for resampling / fitness / ray casting.  Each entry point below names the reference
+ * interface it replaces.  A maintainer binds this library with ctypes (INTEGRATION.md shows the stub);
+ * toss_b200/_native.py is that binding.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  Pointers named d_* are DEVICE pointers owned by
+ *     the caller (torch CUDA tensors in the Python host); h_* are HOST pointers.
+ *   - every function returns 0 on success, non-zero on failure; toss_last_error() gives the message
+ *     (thread-local).  No exceptions cross the ABI.
+ *   - `stream` is a cudaStream_t passed as uintptr_t (0 = legacy default stream).  Calls are
+ *     asynchronous w.r.t. the host unless stated; a context is used from one host thread at a time.
+ *   - FP64 throughout; integer outputs (voxel counts, collision flags) are exact.
+ */
+#ifndef TOSS_B200_H
+#define TOSS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct toss_ctx toss_ctx;
+
+/* The scalar fields of the reference's `args` DotMap that the hot path reads
+ * (toss/resources/default_cfg.toml + derived fields of toss/optimization/setup_parameters.py:49-56). */
+typedef struct {
+    double density;                 /* args.body.density */
+    double spin_axis[3];            /* args.body.spin_axis (normalised on use, as pyquaternion does) */
+    double spin_velocity;           /* args.body.spin_velocity */
+    int32_t activate_rotation;      /* args.problem.activate_rotation */
+    double rtol, atol;              /* args.integrator.rtol / atol */
+    double start_time, final_time;  /* args.problem.start_time / final_time (int32-truncated on use) */
+    double initial_time_step;       /* args.problem.initial_time_step */
+    int32_t activate_event;         /* args.problem.activate_event */
+    int32_t number_of_spacecrafts;  /* args.problem.number_of_spacecrafts (coverage chunking quirk) */
+    double radius_inner;            /* args.problem.radius_inner_bounding_sphere */
+    double radius_outer;            /* args.problem.radius_outer_bounding_sphere */
+    double measurement_period;      /* args.problem.measurement_period */
+    double penalty_scaling_factor;  /* args.problem.penalty_scaling_factor */
+    double target_squared_altitude; /* args.problem.target_squared_altitude */
+    double maximal_measurement_sphere_volume;
+    double total_measurable_volume;
+    int32_t max_steps;              /* per-segment cap on attempted steps (safety; status 1 when hit) */
+    int32_t stop_on_collision;      /* 0 = reference behaviour: integrate to final_time, judge afterwards */
+} toss_params;
+
+/* per-trajectory accounting (throughput metrics: gravity evaluations = n_rhs) */
+typedef struct {
+    int64_t n_rhs;
+    int32_t n_accepted;
+    int32_t n_rejected;
+    int32_t n_event_points;   /* accepted states with |r| <= radius_inner (tested by the ray caster) */
+    int32_t status;           /* 0 ok, 1 step cap, 2 non-finite state, 3 knot capacity exhausted */
+} toss_counters;
+
+/* byte offsets of the arrays inside a propagation workspace (see toss_workspace_layout) */
+typedef struct {
+    size_t knots_t;     /* double [pop][knot_cap]                                              */
+    size_t knots_y;     /* double [pop][knot_cap][6]   accepted states (desolver OdeSystem.y)   */
+    size_t knots_f;     /* double [pop][knot_cap][6]   RHS at the knots (Hermite dense output)  */
+    size_t seg_start;   /* int32  [pop][n_man+2]       first knot of each segment; [n_seg] = n_knots */
+    size_t intervals;   /* double [pop][n_man+2]       integration_intervals                    */
+    size_t n_seg;       /* int32  [pop]                                                        */
+    size_t counters;    /* toss_counters [pop]                                                 */
+    size_t collision;   /* int32  [pop]                collision_detected                      */
+    size_t queue;       /* int32  [4]                  work-queue cursor (internal)            */
+    size_t total_bytes;
+} toss_ws_layout;
+
+const char *toss_version(void);
+const char *toss_last_error(void);
+
+/* One context per process/GPU.  `device` is the CUDA ordinal. */
+int toss_ctx_create(int device, toss_ctx **out);
+int toss_ctx_destroy(toss_ctx *ctx);
+
+/* Replaces polyhedral_gravity.GravityEvaluable((vertices, faces), density)
+ * (toss/optimization/setup_parameters.py:63) and the vertices/faces the ray caster reads
+ * (toss/mesh/mesh_utility.py:70-89).  HOST arrays: verts V x 3 (metres), faces F x 3 (CCW outward).
+ * Precomputes the per-face constants (normal, edge normals, edge lengths, 2*area) on the device. */
+int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t *h_faces, int F, double density);
+int toss_mesh_num_faces(const toss_ctx *ctx);
+
+/* Replaces args.problem.tensor_grid_r/theta/phi + bool_tensor
+ * (toss/fitness/fitness_function_utils.py:231-279).  HOST arrays; bool_tensor is nr*nth*nph bytes. */
+int toss_grid_upload(toss_ctx *ctx, const double *h_r, int nr, const double *h_theta, int nth,
+                     const double *h_phi, int nph, const uint8_t *h_bool_tensor);
+
+/* Replaces args.mesh.evaluable(x, parallel) (equations_of_motion.py:58) for n points at once.
+ * d_pts n x 3 -> d_acc n x 3 in the PACKAGE sign convention (TOSS negates it, :59);
+ * d_pot (n) may be NULL. */
+int toss_gravity_eval(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc, double *d_pot, uintptr_t stream);
+
+/* Replaces compute_motion(t, y, args) (equations_of_motion.py:62-95) for n states: d_t (n), d_y n x 6
+ * -> d_out n x 6 = [v, -gravity(rotate(-w t) r)]. */
+int toss_compute_motion(toss_ctx *ctx, const toss_params *p, const double *d_t, const double *d_y, int64_t n,
+                        double *d_out, uintptr_t stream);
+
+/* workspace for toss_propagate: the caller allocates total_bytes of device memory */
+int toss_workspace_layout(int pop, int n_man, int knot_cap, toss_ws_layout *out);
+
+/* Replaces compute_trajectory(x, args, compute_motion) (compute_trajectory.py:13-162) for a population.
+ * d_x: pop x dim decision vectors (row-major); h_fixed: the n_fixed leading values the UDP prepends
+ * (udp_initial_condition.py:117-120; 0, 3 or 7).  n_fixed + dim must equal 7 + 5 n_man.
+ * Fills the workspace (knots, segments, counters, collision flags). */
+int toss_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim,
+                   const double *h_fixed, int n_fixed, int n_man, void *d_workspace, int knot_cap,
+                   uintptr_t stream);
+
+/* Replaces get_trajectory_fixed_step(args, list_of_ode_objects) (trajectory_tools.py:28-76) for the
+ * trajectories in the workspace: d_pos / d_vel are pop x 3 x N (N = toss_num_samples), d_ts is N. */
+int64_t toss_num_samples(const toss_params *p);
+int toss_resample(toss_ctx *ctx, const toss_params *p, const void *d_workspace, int pop, int n_man, int knot_cap,
+                  double *d_pos, double *d_vel, double *d_ts, uintptr_t stream);
+
+/* Replaces ode_object._OdeSystem__sol(t) (trajectory_tools.py:67): dense output of ONE segment given
+ * its knots (n_knots of t, y[6], f[6]) at nt times -> d_out nt x 6. */
+int toss_dense_eval(toss_ctx *ctx, const double *d_kt, const double *d_ky, const double *d_kf, int n_knots,
+                    const double *d_t, int64_t nt, double *d_out, uintptr_t stream);
+
+/* Replaces get_fitness(enum, args, positions, velocities, timesteps) (fitness_functions.py:7-45) for a
+ * batch: d_pos is batch x 3 x N, d_ts is N; fn = FitnessFunctions value 1..9.
+ * d_fitness (batch); d_n_visited (batch, may be NULL) = number of True voxels after the OR (exact). */
+int toss_fitness_eval(toss_ctx *ctx, int fn, const toss_params *p, const double *d_pos, int batch, int64_t N,
+                      const double *d_ts, double *d_fitness, int64_t *d_n_visited, uintptr_t stream);
+
+/* Replaces update_spherical_tensor_grid(...) (fitness_function_utils.py:165-228): ORs the voxels visited
+ * by ONE trajectory (d_pos 3 x N) into the context's bool_tensor; h_bool_tensor_out (may be NULL)
+ * receives the updated tensor (synchronises the stream). */
+int toss_update_tensor(toss_ctx *ctx, const toss_params *p, const double *d_pos, int64_t N, const double *d_ts,
+                       uint8_t *h_bool_tensor_out, uintptr_t stream);
+
+/* Replaces is_outside(points, vertices, faces) (mesh_utility.py:70-166): d_pts n x 3 -> d_out n bytes,
+ * 1 = outside (even number of +z ray hits). */
+int toss_is_outside(toss_ctx *ctx, const double *d_pts, int64_t n, uint8_t *d_out, uintptr_t stream);
+
+/* Replaces udp_initial_condition.fitness (udp_initial_condition.py:106-137) for a whole population
+ * (the new batch_fitness): propagate -> collision verdict -> resample -> fitness enum 9, with the
+ * resample+fitness fused (positions never materialised).  Device buffers:
+ * d_fitness (pop), d_collision (pop int32, may be NULL), d_counters (pop, may be NULL),
+ * d_n_visited (pop int64, may be NULL; -1 for collided trajectories). */
+int toss_population_fitness(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim,
+                            const double *h_fixed, int n_fixed, int n_man, void *d_workspace, int knot_cap,
+                            double *d_fitness, int32_t *d_collision, toss_counters *d_counters,
+                            int64_t *d_n_visited, uintptr_t stream);
+
+/* Same with HOST buffers (what a pygmo batch_fitness call holds): copies h_x in, runs, copies
+ * h_fitness (and the optional arrays) out and synchronises.  Uses an internal workspace that grows
+ * on demand. */
+int toss_population_fitness_host(toss_ctx *ctx, const toss_params *p, const double *h_x, int pop, int dim,
+                                 const double *h_fixed, int n_fixed, int n_man, int knot_cap,
+                                 double *h_fitness, int32_t *h_collision, toss_counters *h_counters,
+                                 int64_t *h_n_visited);
+
+/* Measures the FP64 FMA peak of the device (register-resident DFMA chains on every SM) in TFLOP/s;
+ * the roofline denominator of bench.py (MEASURED_PEAKS.json has no FP64 entry). */
+int toss_measure_fp64_peak(toss_ctx *ctx, double *tflops_out);
+
+/* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
+int64_t toss_launch_count(const toss_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

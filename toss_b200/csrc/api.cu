@@ -1,0 +1,370 @@
+// toss_b200/csrc/api.cu -- the C ABI of include/toss_b200.h: context, mesh / grid upload, entry points.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+int toss_workspace_layout_impl(int pop, int n_man, int knot_cap, toss_ws_layout *out);
+
+static thread_local std::string g_last_error;
+void toss_set_error(const std::string &msg) { g_last_error = msg; }
+
+extern "C" {
+
+const char *toss_version(void) { return "toss_b200 0.1 (sm_100a)"; }
+const char *toss_last_error(void) { return g_last_error.c_str(); }
+
+int toss_ctx_create(int device, toss_ctx **out)
+{
+    TOSS_REQUIRE(out != nullptr, "toss_ctx_create: out is NULL");
+    int n = 0;
+    TOSS_CHECK_CUDA(cudaGetDeviceCount(&n));
+    TOSS_REQUIRE(device >= 0 && device < n, "toss_ctx_create: no such CUDA device");
+    TOSS_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TOSS_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    TOSS_REQUIRE(prop.major == 10, "toss_ctx_create: this library is built for sm_100a (B200) only");
+    toss_ctx *c = new toss_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    *out = c;
+    return 0;
+}
+
+static void free_mesh(toss_ctx *c)
+{
+    cudaFree(c->d_face_aos);
+    cudaFree(c->d_face_soa);
+    cudaFree(c->d_face_tiles);
+    c->d_face_aos = c->d_face_soa = c->d_face_tiles = nullptr;
+}
+static void free_grid(toss_ctx *c)
+{
+    cudaFree(c->d_grid);
+    cudaFree(c->d_bool_bits);
+    free(c->h_bool);
+    c->d_grid = nullptr;
+    c->d_bool_bits = nullptr;
+    c->h_bool = nullptr;
+}
+
+int toss_ctx_destroy(toss_ctx *ctx)
+{
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    free_mesh(ctx);
+    free_grid(ctx);
+    cudaFree(ctx->d_scratch);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx;
+    return 0;
+}
+
+int toss_mesh_num_faces(const toss_ctx *ctx) { return ctx ? ctx->F : 0; }
+int64_t toss_launch_count(const toss_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// Per-face constants of SURVEY.md App. A.1 (what GravityEvaluable precomputes at construction,
+// setup_parameters.py:63): N = G0 x G1 / |.|, n_q = G_q x N / |.|, |G_q|, 2A = |G0 x G1|.
+int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t *h_faces, int F, double density)
+{
+    TOSS_REQUIRE(ctx && h_verts && h_faces, "toss_mesh_upload: NULL argument");
+    TOSS_REQUIRE(V >= 4 && F >= 4, "toss_mesh_upload: a closed mesh needs at least 4 vertices and 4 faces");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 0; i < 3 * F; ++i)
+        TOSS_REQUIRE(h_faces[i] >= 0 && h_faces[i] < V, "toss_mesh_upload: face index out of range");
+    std::vector<double> rec((size_t)F * kFaceFields);
+    for (int f = 0; f < F; ++f) {
+        double *r = &rec[(size_t)f * kFaceFields];
+        const double *v[3];
+        for (int i = 0; i < 3; ++i) {
+            v[i] = h_verts + 3 * (size_t)h_faces[3 * f + i];
+            for (int c = 0; c < 3; ++c) r[3 * i + c] = v[i][c];
+        }
+        double G[3][3];
+        for (int q = 0; q < 3; ++q)
+            for (int c = 0; c < 3; ++c) G[q][c] = v[(q + 1) % 3][c] - v[q][c];
+        double N[3] = {G[0][1] * G[1][2] - G[0][2] * G[1][1], G[0][2] * G[1][0] - G[0][0] * G[1][2],
+                       G[0][0] * G[1][1] - G[0][1] * G[1][0]};
+        const double nn = sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+        TOSS_REQUIRE(nn > 0.0, "toss_mesh_upload: degenerate (zero-area) face");
+        for (int c = 0; c < 3; ++c) N[c] /= nn;
+        for (int c = 0; c < 3; ++c) r[9 + c] = N[c];
+        for (int q = 0; q < 3; ++q) {
+            const double len = sqrt(G[q][0] * G[q][0] + G[q][1] * G[q][1] + G[q][2] * G[q][2]);
+            double nq[3] = {G[q][1] * N[2] - G[q][2] * N[1], G[q][2] * N[0] - G[q][0] * N[2],
+                            G[q][0] * N[1] - G[q][1] * N[0]};
+            const double nl = sqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2]);
+            for (int c = 0; c < 3; ++c) r[12 + 3 * q + c] = nq[c] / nl;
+            r[21 + q] = len;
+        }
+        r[24] = nn;
+    }
+    auto pad_rec = [](double *r) {
+        for (int k = 0; k < kFaceFields; ++k) r[k] = 0.0;
+        for (int k = 0; k < 9; ++k) r[k] = kPadVertex;
+    };
+    free_mesh(ctx);
+    ctx->V = V;
+    ctx->F = F;
+    ctx->Grho = kGravConst * density;
+    ctx->Fpad32 = (F + 31) / 32 * 32;
+    ctx->n_aos_tiles = (F + kAosTileFaces - 1) / kAosTileFaces;
+    ctx->n_soa_tiles = (F + kSoaTileFaces - 1) / kSoaTileFaces;
+
+    // (1) AoS, 26 doubles per face, padded to whole 64-face tiles      -> K1 thread-per-point
+    std::vector<double> aos((size_t)ctx->n_aos_tiles * kAosTileFaces * kAosStride, 0.0);
+    for (int f = 0; f < ctx->n_aos_tiles * kAosTileFaces; ++f) {
+        double tmp[kFaceFields];
+        if (f < F) memcpy(tmp, &rec[(size_t)f * kFaceFields], sizeof(tmp));
+        else pad_rec(tmp);
+        memcpy(&aos[(size_t)f * kAosStride], tmp, sizeof(tmp));
+    }
+    // (2) flat SoA [25][Fpad32]                                          -> resident stepper, K1b, K5
+    std::vector<double> soa((size_t)kFaceFields * ctx->Fpad32);
+    for (int f = 0; f < ctx->Fpad32; ++f) {
+        double tmp[kFaceFields];
+        if (f < F) memcpy(tmp, &rec[(size_t)f * kFaceFields], sizeof(tmp));
+        else pad_rec(tmp);
+        for (int k = 0; k < kFaceFields; ++k) soa[(size_t)k * ctx->Fpad32 + f] = tmp[k];
+    }
+    // (3) tiled SoA [n_tiles][25][128] -> streaming stepper.  Face f sits in tile f/128, slot f%128, so lane l
+    //     still owns faces l, l+32, l+64, ... in increasing order: the same summation order as the flat layout.
+    std::vector<double> tiles((size_t)ctx->n_soa_tiles * kSoaTileDoubles);
+    for (int t = 0; t < ctx->n_soa_tiles; ++t)
+        for (int j = 0; j < kSoaTileFaces; ++j) {
+            const int f = t * kSoaTileFaces + j;
+            double tmp[kFaceFields];
+            if (f < F) memcpy(tmp, &rec[(size_t)f * kFaceFields], sizeof(tmp));
+            else pad_rec(tmp);
+            for (int k = 0; k < kFaceFields; ++k) tiles[((size_t)t * kFaceFields + k) * kSoaTileFaces + j] = tmp[k];
+        }
+    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_face_aos, aos.size() * 8));
+    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_face_soa, soa.size() * 8));
+    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_face_tiles, tiles.size() * 8));
+    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_face_aos, aos.data(), aos.size() * 8, cudaMemcpyHostToDevice));
+    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_face_soa, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice));
+    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_face_tiles, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int upload_bool_bits(toss_ctx *ctx)
+{
+    const long long nvox = (long long)ctx->nr * ctx->nth * ctx->nph;
+    const size_t nw = (size_t)((nvox + 31) / 32);
+    std::vector<uint32_t> bits(nw, 0u);
+    for (long long b = 0; b < nvox; ++b)
+        if (ctx->h_bool[b]) bits[b >> 5] |= 1u << (b & 31);
+    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_bool_bits, bits.data(), nw * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int toss_grid_upload(toss_ctx *ctx, const double *h_r, int nr, const double *h_theta, int nth, const double *h_phi,
+                     int nph, const uint8_t *h_bool_tensor)
+{
+    TOSS_REQUIRE(ctx && h_r && h_theta && h_phi && h_bool_tensor, "toss_grid_upload: NULL argument");
+    TOSS_REQUIRE(nr >= 1 && nth >= 1 && nph >= 1, "toss_grid_upload: empty grid axis");
+    TOSS_REQUIRE((long long)nr * nth * nph < (1LL << 31), "toss_grid_upload: grid too large");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    free_grid(ctx);
+    ctx->nr = nr;
+    ctx->nth = nth;
+    ctx->nph = nph;
+    const size_t nvox = (size_t)nr * nth * nph;
+    std::vector<double> g;
+    g.insert(g.end(), h_r, h_r + nr);
+    g.insert(g.end(), h_theta, h_theta + nth);
+    g.insert(g.end(), h_phi, h_phi + nph);
+    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_grid, g.size() * 8));
+    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_grid, g.data(), g.size() * 8, cudaMemcpyHostToDevice));
+    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_bool_bits, ((nvox + 31) / 32) * 4));
+    ctx->h_bool = (uint8_t *)malloc(nvox);
+    memcpy(ctx->h_bool, h_bool_tensor, nvox);
+    return upload_bool_bits(ctx);
+}
+
+int toss_gravity_eval(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc, double *d_pot, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx != nullptr, "toss_gravity_eval: NULL context");
+    TOSS_REQUIRE(n == 0 || (d_pts && d_acc), "toss_gravity_eval: NULL buffer");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_gravity(ctx, d_pts, n, d_acc, d_pot, (cudaStream_t)stream);
+}
+
+int toss_compute_motion(toss_ctx *ctx, const toss_params *p, const double *d_t, const double *d_y, int64_t n,
+                        double *d_out, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && p, "toss_compute_motion: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_compute_motion(ctx, p, d_t, d_y, n, d_out, (cudaStream_t)stream);
+}
+
+int toss_workspace_layout(int pop, int n_man, int knot_cap, toss_ws_layout *out)
+{
+    TOSS_REQUIRE(out && pop > 0 && n_man >= 0 && knot_cap > 0, "toss_workspace_layout: bad argument");
+    return toss_workspace_layout_impl(pop, n_man, knot_cap, out);
+}
+
+int toss_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
+                   int n_fixed, int n_man, void *d_workspace, int knot_cap, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && p && d_workspace && (d_x || dim == 0), "toss_propagate: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    if (int rc = launch_propagate(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_workspace, knot_cap,
+                                  (cudaStream_t)stream))
+        return rc;
+    return launch_collision(ctx, p, d_workspace, pop, n_man, knot_cap, (cudaStream_t)stream);
+}
+
+int64_t toss_num_samples(const toss_params *p)
+{   // len(np.arange(start, final, period))  (trajectory_tools.py:46)
+    const double n = ceil((p->final_time - p->start_time) / p->measurement_period);
+    return n > 0 ? (int64_t)n : 0;
+}
+
+int toss_resample(toss_ctx *ctx, const toss_params *p, const void *d_workspace, int pop, int n_man, int knot_cap,
+                  double *d_pos, double *d_vel, double *d_ts, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && p && d_workspace && d_pos, "toss_resample: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_resample(ctx, p, d_workspace, pop, n_man, knot_cap, d_pos, d_vel, d_ts, (cudaStream_t)stream);
+}
+
+int toss_dense_eval(toss_ctx *ctx, const double *d_kt, const double *d_ky, const double *d_kf, int n_knots,
+                    const double *d_t, int64_t nt, double *d_out, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && d_kt && d_ky && d_kf && d_t && d_out, "toss_dense_eval: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_dense_eval(ctx, d_kt, d_ky, d_kf, n_knots, d_t, nt, d_out, (cudaStream_t)stream);
+}
+
+int toss_fitness_eval(toss_ctx *ctx, int fn, const toss_params *p, const double *d_pos, int batch, int64_t N,
+                      const double *d_ts, double *d_fitness, int64_t *d_n_visited, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && p && d_pos && d_ts && d_fitness, "toss_fitness_eval: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_fitness_positions(ctx, fn, p, d_pos, batch, N, d_ts, d_fitness, d_n_visited, nullptr,
+                                    (cudaStream_t)stream);
+}
+
+int toss_update_tensor(toss_ctx *ctx, const toss_params *p, const double *d_pos, int64_t N, const double *d_ts,
+                       uint8_t *h_bool_tensor_out, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && p && d_pos && d_ts, "toss_update_tensor: NULL argument");
+    TOSS_REQUIRE(ctx->d_grid != nullptr, "toss_update_tensor: no voxel grid uploaded");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nvox = (long long)ctx->nr * ctx->nth * ctx->nph;
+    const size_t nw = (size_t)((nvox + 31) / 32);
+    double *d_fit = nullptr;
+    uint32_t *d_bits = nullptr;
+    TOSS_CHECK_CUDA(cudaMalloc(&d_fit, 8));
+    TOSS_CHECK_CUDA(cudaMalloc(&d_bits, nw * 4));
+    int rc = launch_fitness_positions(ctx, 8, p, d_pos, 1, N, d_ts, d_fit, nullptr, d_bits, st);
+    std::vector<uint32_t> bits(nw);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(bits.data(), d_bits, nw * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            toss_set_error(std::string("toss_update_tensor: ") + cudaGetErrorString(e));
+            rc = 1;
+        }
+    }
+    cudaFree(d_fit);
+    cudaFree(d_bits);
+    if (rc) return rc;
+    for (long long b = 0; b < nvox; ++b) ctx->h_bool[b] = (bits[b >> 5] >> (b & 31)) & 1u;
+    if (h_bool_tensor_out) memcpy(h_bool_tensor_out, ctx->h_bool, (size_t)nvox);
+    return upload_bool_bits(ctx);
+}
+
+int toss_is_outside(toss_ctx *ctx, const double *d_pts, int64_t n, uint8_t *d_out, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && (n == 0 || (d_pts && d_out)), "toss_is_outside: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_is_outside(ctx, d_pts, n, d_out, (cudaStream_t)stream);
+}
+
+int toss_population_fitness(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim,
+                            const double *h_fixed, int n_fixed, int n_man, void *d_workspace, int knot_cap,
+                            double *d_fitness, int32_t *d_collision, toss_counters *d_counters, int64_t *d_n_visited,
+                            uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && p && d_workspace && d_fitness, "toss_population_fitness: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = launch_propagate(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_workspace, knot_cap, st)) return rc;
+    if (int rc = launch_collision(ctx, p, d_workspace, pop, n_man, knot_cap, st)) return rc;
+    return launch_fitness_knots(ctx, p, d_workspace, pop, n_man, knot_cap, d_fitness, d_collision, d_counters,
+                                d_n_visited, st);
+}
+
+int toss_population_fitness_host(toss_ctx *ctx, const toss_params *p, const double *h_x, int pop, int dim,
+                                 const double *h_fixed, int n_fixed, int n_man, int knot_cap, double *h_fitness,
+                                 int32_t *h_collision, toss_counters *h_counters, int64_t *h_n_visited)
+{
+    TOSS_REQUIRE(ctx && p && h_fitness && (h_x || dim == 0), "toss_population_fitness_host: NULL argument");
+    TOSS_REQUIRE(pop > 0, "toss_population_fitness_host: empty population");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    toss_ws_layout L;
+    toss_workspace_layout_impl(pop, n_man, knot_cap, &L);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_x = up(L.total_bytes);
+    const size_t o_fit = up(o_x + sizeof(double) * (size_t)pop * (dim > 0 ? dim : 1));
+    const size_t o_coll = up(o_fit + sizeof(double) * pop);
+    const size_t o_cnt = up(o_coll + sizeof(int32_t) * pop);
+    const size_t o_nv = up(o_cnt + sizeof(toss_counters) * pop);
+    const size_t total = up(o_nv + sizeof(int64_t) * pop);
+    if (ctx->scratch_bytes < total) {
+        cudaFree(ctx->d_scratch);
+        ctx->d_scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_scratch, total));
+        ctx->scratch_bytes = total;
+    }
+    // pinned staging: [x | fitness | collision | counters | n_visited]
+    const size_t hp_x = 0, hp_fit = up(sizeof(double) * (size_t)pop * (dim > 0 ? dim : 1));
+    const size_t hp_coll = up(hp_fit + sizeof(double) * pop), hp_cnt = up(hp_coll + sizeof(int32_t) * pop);
+    const size_t hp_nv = up(hp_cnt + sizeof(toss_counters) * pop), hp_total = up(hp_nv + sizeof(int64_t) * pop);
+    if (ctx->pinned_bytes < hp_total) {
+        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        ctx->h_pinned = nullptr;
+        ctx->pinned_bytes = 0;
+        TOSS_CHECK_CUDA(cudaMallocHost(&ctx->h_pinned, hp_total));
+        ctx->pinned_bytes = hp_total;
+    }
+    unsigned char *ws = static_cast<unsigned char *>(ctx->d_scratch);
+    unsigned char *hp = static_cast<unsigned char *>(ctx->h_pinned);
+    cudaStream_t st = 0;
+    if (dim > 0) {
+        memcpy(hp + hp_x, h_x, sizeof(double) * (size_t)pop * dim);
+        TOSS_CHECK_CUDA(cudaMemcpyAsync(ws + o_x, hp + hp_x, sizeof(double) * (size_t)pop * dim, cudaMemcpyHostToDevice, st));
+    }
+    if (int rc = toss_population_fitness(ctx, p, reinterpret_cast<double *>(ws + o_x), pop, dim, h_fixed, n_fixed, n_man,
+                                         ws, knot_cap, reinterpret_cast<double *>(ws + o_fit),
+                                         reinterpret_cast<int32_t *>(ws + o_coll),
+                                         reinterpret_cast<toss_counters *>(ws + o_cnt),
+                                         reinterpret_cast<int64_t *>(ws + o_nv), (uintptr_t)st))
+        return rc;
+    TOSS_CHECK_CUDA(cudaMemcpyAsync(hp + hp_fit, ws + o_fit, sizeof(double) * pop, cudaMemcpyDeviceToHost, st));
+    if (h_collision) TOSS_CHECK_CUDA(cudaMemcpyAsync(hp + hp_coll, ws + o_coll, sizeof(int32_t) * pop, cudaMemcpyDeviceToHost, st));
+    if (h_counters) TOSS_CHECK_CUDA(cudaMemcpyAsync(hp + hp_cnt, ws + o_cnt, sizeof(toss_counters) * pop, cudaMemcpyDeviceToHost, st));
+    if (h_n_visited) TOSS_CHECK_CUDA(cudaMemcpyAsync(hp + hp_nv, ws + o_nv, sizeof(int64_t) * pop, cudaMemcpyDeviceToHost, st));
+    TOSS_CHECK_CUDA(cudaStreamSynchronize(st));
+    memcpy(h_fitness, hp + hp_fit, sizeof(double) * pop);
+    if (h_collision) memcpy(h_collision, hp + hp_coll, sizeof(int32_t) * pop);
+    if (h_counters) memcpy(h_counters, hp + hp_cnt, sizeof(toss_counters) * pop);
+    if (h_n_visited) memcpy(h_n_visited, hp + hp_nv, sizeof(int64_t) * pop);
+    return 0;
+}
+
+int toss_measure_fp64_peak(toss_ctx *ctx, double *tflops_out)
+{
+    TOSS_REQUIRE(ctx && tflops_out, "toss_measure_fp64_peak: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_fp64_peak(ctx, tflops_out);
+}
+
+}   // extern "C"

@@ -1,0 +1,267 @@
+// toss_b200/csrc/gravity_kernels.cu -- K1: batched polyhedral gravity; batched RHS; point-in-polyhedron; DFMA peak.
+#include "gravity.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// K1a  thread-per-point.  One CTA = 128 field points.  The face records (AoS, 208 B) stream through a
+// 4-stage shared-memory ring filled by TMA bulk copies (one 13 KB tile = 64 faces per copy); every
+// lane reads the SAME record (LDS.128 broadcast), so there is no reduction at all: each thread owns
+// its accumulator.  FP64-pipe bound: ~1 smem wavefront per ~20 DFMA-pipe instructions.
+// ------------------------------------------------------------------------------------------------
+constexpr int kK1Threads = 128;
+constexpr int kK1Stages = 4;
+constexpr int kAosTileBytes = kAosTileFaces * kAosStride * 8;
+
+template <bool kPot>
+__global__ void __launch_bounds__(kK1Threads, 4)
+gravity_points_kernel(const double *__restrict__ face_aos, int n_tiles, const double *__restrict__ pts, int64_t n,
+                      double *__restrict__ acc, double *__restrict__ pot, double Grho)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *tiles = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kK1Stages * kAosTileBytes);
+    uint64_t *empty = full + kK1Stages;
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kK1Stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kK1Threads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int pre = n_tiles < kK1Stages ? n_tiles : kK1Stages;
+        for (int s = 0; s < pre; ++s) {
+            mbar_arrive_expect_tx(&full[s], kAosTileBytes);
+            tma_load_1d(tiles + (size_t)s * kAosTileFaces * kAosStride, face_aos + (size_t)s * kAosTileFaces * kAosStride,
+                        kAosTileBytes, &full[s]);
+        }
+    }
+
+    const int64_t i = (int64_t)blockIdx.x * kK1Threads + tid;
+    const int64_t ic = i < n ? i : n - 1;   // tail threads shadow the last point (keeps the warp converged)
+    const double Px = pts[3 * ic], Py = pts[3 * ic + 1], Pz = pts[3 * ic + 2];
+    double ax = 0.0, ay = 0.0, az = 0.0, pv = 0.0;
+
+    for (int it = 0; it < n_tiles; ++it) {
+        const int s = it % kK1Stages;
+        const uint32_t ph = (uint32_t)(it / kK1Stages) & 1u;
+        // refill the stage consumed one iteration ago (gives the other warps a whole tile to release it)
+        if (tid == 0 && it >= 1) {
+            const int prev = it - 1, nxt = prev + kK1Stages;
+            if (nxt < n_tiles) {
+                const int ps = prev % kK1Stages;
+                mbar_wait(&empty[ps], (uint32_t)(prev / kK1Stages) & 1u);
+                mbar_arrive_expect_tx(&full[ps], kAosTileBytes);
+                tma_load_1d(tiles + (size_t)ps * kAosTileFaces * kAosStride,
+                            face_aos + (size_t)nxt * kAosTileFaces * kAosStride, kAosTileBytes, &full[ps]);
+            }
+        }
+        mbar_wait(&full[s], ph);
+        const double *tile = tiles + (size_t)s * kAosTileFaces * kAosStride;
+#pragma unroll 2
+        for (int f = 0; f < kAosTileFaces; ++f) {
+            const double *rec = tile + f * kAosStride;
+            face_term<kPot>([rec](int k) { return rec[k]; }, Px, Py, Pz, ax, ay, az, pv);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    if (i < n) {
+        acc[3 * i] = Grho * ax;
+        acc[3 * i + 1] = Grho * ay;
+        acc[3 * i + 2] = Grho * az;
+        if (kPot) pot[i] = 0.5 * Grho * pv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1b  warp-per-point (few points: the single-point `evaluable(x)` call, compute_motion batches):
+// lanes stride the faces of the flat SoA (coalesced 256 B loads), butterfly-shuffle reduction.
+// Same lane->face map and reduction tree as the stepper, so values are identical to the RHS it sees.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_gravity_global(const double *__restrict__ soa, int Fpad32, double Px, double Py,
+                                                    double Pz, int lane, double &ax, double &ay, double &az,
+                                                    double &pv)
+{
+    ax = ay = az = pv = 0.0;
+    for (int f = lane; f < Fpad32; f += 32) {
+        const double *col = soa + f;
+        face_term<true>([col, Fpad32](int k) { return __ldg(col + (size_t)k * Fpad32); }, Px, Py, Pz, ax, ay, az, pv);
+    }
+    ax = warp_sum(ax);
+    ay = warp_sum(ay);
+    az = warp_sum(az);
+    pv = warp_sum(pv);
+}
+
+__global__ void __launch_bounds__(256) gravity_warp_kernel(const double *__restrict__ soa, int Fpad32,
+                                                           const double *__restrict__ pts, int64_t n,
+                                                           double *__restrict__ acc, double *__restrict__ pot,
+                                                           double Grho)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n) return;
+    double ax, ay, az, pv;
+    warp_gravity_global(soa, Fpad32, pts[3 * w], pts[3 * w + 1], pts[3 * w + 2], lane, ax, ay, az, pv);
+    if (lane == 0) {
+        acc[3 * w] = Grho * ax;
+        acc[3 * w + 1] = Grho * ay;
+        acc[3 * w + 2] = Grho * az;
+        if (pot) pot[w] = 0.5 * Grho * pv;
+    }
+}
+
+// equations_of_motion.py:62-95 for a batch of (t, y): rotate r by -w t, gravity there, NOT rotated back.
+__global__ void __launch_bounds__(256) compute_motion_kernel(const double *__restrict__ soa, int Fpad32, double Grho,
+                                                             UnitAxis k, double w, int rotate,
+                                                             const double *__restrict__ ts,
+                                                             const double *__restrict__ ys, int64_t n,
+                                                             double *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const double *y = ys + 6 * i;
+    double px = y[0], py = y[1], pz = y[2];
+    if (rotate) rotate_point_dev(ts[i], y[0], y[1], y[2], k.x, k.y, k.z, w, px, py, pz);
+    double ax, ay, az, pv;
+    warp_gravity_global(soa, Fpad32, px, py, pz, lane, ax, ay, az, pv);
+    if (lane == 0) {
+        double *o = out + 6 * i;
+        o[0] = y[3];
+        o[1] = y[4];
+        o[2] = y[5];
+        o[3] = -(Grho * ax);
+        o[4] = -(Grho * ay);
+        o[5] = -(Grho * az);
+    }
+}
+
+// K5 standalone: mesh_utility.py:70-89.  Warp per point, lanes stride the faces, integer hit count.
+__global__ void __launch_bounds__(256) is_outside_kernel(const double *__restrict__ soa, int Fpad32,
+                                                         const double *__restrict__ pts, int64_t n,
+                                                         uint8_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const double ox = pts[3 * i], oy = pts[3 * i + 1], oz = pts[3 * i + 2];
+    int hits = 0;
+    for (int f = lane; f < Fpad32; f += 32) {
+        const double *c = soa + f;
+        const size_t S = (size_t)Fpad32;
+        hits += ray_hits_dev(ox, oy, oz, c[0], c[S], c[2 * S], c[3 * S], c[4 * S], c[5 * S], c[6 * S], c[7 * S],
+                             c[8 * S]);
+    }
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    if (lane == 0) out[i] = (uint8_t)((hits & 1) == 0);
+}
+
+// Register-resident DFMA chains on every SM: the FP64 roofline denominator measured on the box.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c);
+            a1 = fma(a1, m, c);
+            a2 = fma(a2, m, c);
+            a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c);
+            a5 = fma(a5, m, c);
+            a6 = fma(a6, m, c);
+            a7 = fma(a7, m, c);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// ---------------------------------------- launchers ---------------------------------------------
+int launch_gravity(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc, double *d_pot, cudaStream_t st)
+{
+    TOSS_REQUIRE(ctx && ctx->d_face_aos, "toss_gravity_eval: no mesh uploaded");
+    if (n <= 0) return 0;
+    if (n < 4096) {   // not enough points to fill the machine with one thread each
+        const int64_t threads = n * 32;
+        const int64_t blocks = (threads + 255) / 256;
+        gravity_warp_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_face_soa, ctx->Fpad32, d_pts, n, d_acc, d_pot,
+                                                            ctx->Grho);
+    } else {
+        const size_t smem = (size_t)kK1Stages * kAosTileBytes + 2 * kK1Stages * sizeof(uint64_t);
+        const int64_t blocks = (n + kK1Threads - 1) / kK1Threads;
+        TOSS_REQUIRE(blocks < 2147483647LL, "toss_gravity_eval: too many points for one launch");
+        if (d_pot) {
+            TOSS_CHECK_CUDA(cudaFuncSetAttribute(gravity_points_kernel<true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gravity_points_kernel<true><<<(unsigned)blocks, kK1Threads, smem, st>>>(ctx->d_face_aos, ctx->n_aos_tiles,
+                                                                                  d_pts, n, d_acc, d_pot, ctx->Grho);
+        } else {
+            TOSS_CHECK_CUDA(cudaFuncSetAttribute(gravity_points_kernel<false>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gravity_points_kernel<false><<<(unsigned)blocks, kK1Threads, smem, st>>>(
+                ctx->d_face_aos, ctx->n_aos_tiles, d_pts, n, d_acc, nullptr, ctx->Grho);
+        }
+    }
+    ctx->launches++;
+    TOSS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_compute_motion(toss_ctx *ctx, const toss_params *p, const double *d_t, const double *d_y, int64_t n,
+                          double *d_out, cudaStream_t st)
+{
+    TOSS_REQUIRE(ctx && ctx->d_face_soa, "toss_compute_motion: no mesh uploaded");
+    if (n <= 0) return 0;
+    const int64_t blocks = (n * 32 + 255) / 256;
+    compute_motion_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_face_soa, ctx->Fpad32, ctx->Grho,
+                                                          unit_axis_host(p->spin_axis), p->spin_velocity,
+                                                          p->activate_rotation, d_t, d_y, n, d_out);
+    ctx->launches++;
+    TOSS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_is_outside(toss_ctx *ctx, const double *d_pts, int64_t n, uint8_t *d_out, cudaStream_t st)
+{
+    TOSS_REQUIRE(ctx && ctx->d_face_soa, "toss_is_outside: no mesh uploaded");
+    if (n <= 0) return 0;
+    const int64_t blocks = (n * 32 + 255) / 256;
+    is_outside_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_face_soa, ctx->Fpad32, d_pts, n, d_out);
+    ctx->launches++;
+    TOSS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_fp64_peak(toss_ctx *ctx, double *tflops)
+{
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    double *d_out = nullptr;
+    TOSS_CHECK_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    TOSS_CHECK_CUDA(cudaEventCreate(&e0));
+    TOSS_CHECK_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        TOSS_CHECK_CUDA(cudaEventRecord(e0));
+        dfma_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0 + rep);
+        TOSS_CHECK_CUDA(cudaEventRecord(e1));
+        TOSS_CHECK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        TOSS_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep >= 1 && tf > best) best = tf;
+        ctx->launches++;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
+    return 0;
+}

@@ -1,0 +1,445 @@
+// toss_b200/csrc/stepper.cu -- K2: population-parallel RK8(7)-13M (the reference's "DOP853" slot:
+// desolver RK8713MSolver, toss/trajectory/Integrator.py:14) through the polyhedral gravity field.
+//
+// Replaces compute_trajectory -> integrate_system -> desolver OdeSystem.integrate
+// (toss/trajectory/compute_trajectory.py:13-162, 203-261) for a whole population.
+//
+// One warp per trajectory.  Lanes 0..5 own the six state components (y_c, k_j[c]); for every RHS
+// evaluation the 32 lanes split the faces (lane -> faces lane, lane+32, ...), accumulate in a fixed
+// order and butterfly-reduce, so a trajectory's arithmetic does not depend on the population around
+// it.  Warps pull trajectories from an atomic queue and retire them independently (finished, step
+// cap, non-finite state, knot capacity).
+//
+// Two mesh-staging modes:
+//   RESIDENT  the flat SoA face table fits in shared memory (lllp, llp): TMA-copied once per CTA;
+//             warps then run completely independently.
+//   STREAM    (lp, full) the table streams through a 3-stage ring of 25.6 KB SoA tiles filled by TMA
+//             bulk copies; the 8 warps of a CTA sweep the tiles in lock step (one RHS evaluation per
+//             warp per sweep) so every byte fetched from L2 is used by 8 trajectories.
+#include "gravity.cuh"
+
+#define TOSS_RK_QUAL __constant__
+#include "rk8713m_tableau.h"
+
+constexpr int kK2Warps = 8;
+constexpr int kK2Threads = kK2Warps * 32;
+constexpr int kK2Stages = 3;
+constexpr int kSoaTileBytes = kSoaTileDoubles * 8;
+
+struct StepArgs {
+    toss_params p;
+    UnitAxis axis;
+    double Grho;
+    const double *face_soa;    // [25][Fpad32]           (RESIDENT)
+    const double *face_tiles;  // [n_tiles][25][128]     (STREAM)
+    int Fpad32, n_tiles;
+    const double *x;           // pop x dim
+    int pop, dim, n_fixed, n_man, knot_cap;
+    double fixed[8];
+    // workspace
+    double *knots_t, *knots_y, *knots_f, *intervals;
+    int32_t *seg_start, *n_seg, *collision, *queue;
+    toss_counters *counters;
+};
+
+// per-warp shared state (doubles): y[6] | k[13][6] | meta[2] | seg_t[n_man+2] | dv[3*n_man]
+__host__ __device__ inline int warp_state_doubles(int n_man) { return 6 + 78 + 2 + (n_man + 2) + 3 * (n_man > 0 ? n_man : 1); }
+
+template <bool kStream>
+__global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int mesh_doubles = kStream ? kK2Stages * kSoaTileDoubles : kFaceFields * a.Fpad32;
+    double *mesh = reinterpret_cast<double *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(mesh + mesh_doubles);   // full[3] empty[3] (STREAM) / full[1]
+    double *wstate = reinterpret_cast<double *>(bars + 8) + (size_t)wid * warp_state_doubles(a.n_man);
+    double *sy = wstate, *sk = wstate + 6, *meta = wstate + 84, *seg_t = wstate + 86, *sdv = seg_t + (a.n_man + 2);
+
+    if (tid == 0) {
+        if (kStream) {
+            for (int s = 0; s < kK2Stages; ++s) {
+                mbar_init(&bars[s], 1);
+                mbar_init(&bars[kK2Stages + s], kK2Warps);
+            }
+        } else {
+            mbar_init(&bars[0], 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    uint32_t issued = 0;      // tiles issued by the producer thread (tid 0), STREAM only
+    if (tid == 0) {
+        if (kStream) {
+            for (int s = 0; s < kK2Stages; ++s) {   // the ring is cyclic over the mesh: always something to fetch
+                mbar_arrive_expect_tx(&bars[s], kSoaTileBytes);
+                tma_load_1d(mesh + (size_t)s * kSoaTileDoubles,
+                            a.face_tiles + (size_t)(issued % a.n_tiles) * kSoaTileDoubles, kSoaTileBytes, &bars[s]);
+                ++issued;
+            }
+        } else {
+            const uint32_t bytes = (uint32_t)mesh_doubles * 8u;
+            mbar_arrive_expect_tx(&bars[0], bytes);
+            uint32_t off = 0;   // bulk copies are capped well below 1 MB each; chunk to be safe
+            while (off < bytes) {
+                const uint32_t c = bytes - off < 65536u ? bytes - off : 65536u;
+                tma_load_1d(reinterpret_cast<unsigned char *>(mesh) + off,
+                            reinterpret_cast<const unsigned char *>(a.face_soa) + off, c, &bars[0]);
+                off += c;
+            }
+        }
+    }
+    if (!kStream) mbar_wait(&bars[0], 0);
+
+    const toss_params &p = a.p;
+    const double R2 = mul_(p.radius_inner, p.radius_inner);
+    uint32_t tile_it = 0;     // tiles consumed so far by this warp (== by every warp: lock step)
+
+    // warp-uniform trajectory state
+    bool active = false, queue_empty = false;
+    int traj = -1, stage = 0, seg = 0, nseg = 0, nk = 0, steps = 0, clipped = 0, after_accept = 0, status = 0;
+    int n_acc = 0, n_rej = 0, n_ev = 0;
+    long long n_rhs = 0;
+    double t = 0.0, dt = 0.0, tf = 0.0;
+
+    for (;;) {
+        // ------------------------------------------------ fetch a trajectory, decode the chromosome
+        if (!active && !queue_empty) {
+            int nxt = 0;
+            if (lane == 0) nxt = atomicAdd(a.queue, 1);
+            nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            if (nxt >= a.pop) {
+                queue_empty = true;
+            } else {
+                traj = nxt;
+                active = true;
+                // x = hstack(initial_condition, chromosome)  (udp_initial_condition.py:117-120)
+                auto X = [&](int i) -> double {
+                    return i < a.n_fixed ? a.fixed[i] : a.x[(size_t)traj * a.dim + (i - a.n_fixed)];
+                };
+                // compute_trajectory.py:53-55: v0 = v_mag * v_dir (direction NOT normalised)
+                if (lane < 3) sy[lane] = X(lane);
+                else if (lane < 6) sy[lane] = mul_(X(3), X(lane + 1));
+                // compute_trajectory.py:75-121: int32 truncation, stable sort, equal times merged (dv summed)
+                if (lane == 0) {
+                    const int M = a.n_man;
+                    int idx[64];
+                    int32_t tm[64];
+                    for (int k = 0; k < M; ++k) {
+                        tm[k] = (int32_t)X(7 + 5 * k);
+                        idx[k] = k;
+                    }
+                    for (int i = 1; i < M; ++i) {
+                        int j = i, v = idx[i];
+                        while (j > 0 && tm[idx[j - 1]] > tm[v]) {
+                            idx[j] = idx[j - 1];
+                            --j;
+                        }
+                        idx[j] = v;
+                    }
+                    int n = 0;
+                    seg_t[0] = (double)(int32_t)p.start_time;
+                    for (int i = 0; i < M; ++i) {
+                        const int k = idx[i];
+                        const double mag = X(8 + 5 * k);
+                        const double dx = mul_(mag, X(9 + 5 * k)), dy = mul_(mag, X(10 + 5 * k)),
+                                     dz = mul_(mag, X(11 + 5 * k));
+                        if (n > 0 && (double)tm[k] == seg_t[n]) {
+                            sdv[3 * (n - 1)] = add_(sdv[3 * (n - 1)], dx);
+                            sdv[3 * (n - 1) + 1] = add_(sdv[3 * (n - 1) + 1], dy);
+                            sdv[3 * (n - 1) + 2] = add_(sdv[3 * (n - 1) + 2], dz);
+                        } else {
+                            seg_t[n + 1] = (double)tm[k];
+                            sdv[3 * n] = dx;
+                            sdv[3 * n + 1] = dy;
+                            sdv[3 * n + 2] = dz;
+                            ++n;
+                        }
+                    }
+                    seg_t[n + 1] = (double)(int32_t)p.final_time;
+                    a.n_seg[traj] = n + 1;
+                    for (int s = 0; s <= n + 1; ++s) a.intervals[(size_t)traj * (a.n_man + 2) + s] = seg_t[s];
+                    meta[0] = (double)(n + 1);   // segment count travels to the other lanes through shared memory
+                }
+                __syncwarp();
+                nseg = (int)meta[0];
+                __syncwarp();
+                seg = 0;
+                t = seg_t[0];
+                tf = seg_t[1];
+                dt = p.initial_time_step;
+                stage = 0;
+                nk = 0;
+                steps = 0;
+                clipped = 0;
+                after_accept = 0;
+                status = 0;
+                n_acc = n_rej = n_ev = 0;
+                n_rhs = 0;
+                if (lane == 0) a.seg_start[(size_t)traj * (a.n_man + 2)] = 0;
+            }
+        }
+        if (kStream) {
+            if (!__syncthreads_or(active ? 1 : 0)) break;
+        } else {
+            if (!active) break;
+        }
+
+        // ------------------------------------------------ stage point: ys = y + dt sum_j a_ij k_j
+        double ysc = 0.0, te = t;
+        if (active) {
+            if (lane < 6) {
+                ysc = sy[lane];
+                if (stage > 0) {
+                    double s = 0.0;
+                    for (int j = 0; j < stage; ++j) s = add_(s, mul_(TOSS_RK_A[13 * stage + j], sk[6 * j + lane]));
+                    ysc = add_(ysc, mul_(dt, s));
+                }
+            }
+            if (stage > 0) te = add_(t, mul_(TOSS_RK_C[stage], dt));
+        }
+        const double qx = __shfl_sync(0xffffffffu, ysc, 0), qy = __shfl_sync(0xffffffffu, ysc, 1),
+                     qz = __shfl_sync(0xffffffffu, ysc, 2);
+        const double vsh = __shfl_sync(0xffffffffu, ysc, (lane + 3) & 31);   // lanes 0..2 receive ys[3..5]
+        double Px = qx, Py = qy, Pz = qz;
+        if (active && p.activate_rotation)
+            rotate_point_dev(te, qx, qy, qz, a.axis.x, a.axis.y, a.axis.z, p.spin_velocity, Px, Py, Pz);
+
+        // ------------------------------------------------ gravity sweep over all faces
+        double ax = 0.0, ay = 0.0, az = 0.0, pv = 0.0;
+        if (kStream) {
+            for (int tl = 0; tl < a.n_tiles; ++tl, ++tile_it) {
+                const int s = tile_it % kK2Stages;
+                if (tid == 0 && tile_it >= 1) {   // refill the stage released one tile ago
+                    const uint32_t prev = tile_it - 1;
+                    const int ps = prev % kK2Stages;
+                    mbar_wait(&bars[kK2Stages + ps], (prev / kK2Stages) & 1u);
+                    mbar_arrive_expect_tx(&bars[ps], kSoaTileBytes);
+                    tma_load_1d(mesh + (size_t)ps * kSoaTileDoubles,
+                                a.face_tiles + (size_t)(issued % a.n_tiles) * kSoaTileDoubles, kSoaTileBytes,
+                                &bars[ps]);
+                    ++issued;
+                }
+                mbar_wait(&bars[s], (tile_it / kK2Stages) & 1u);
+                if (active) {
+                    const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
+#pragma unroll 2
+                    for (int f = 0; f < kSoaTileFaces; f += 32) {
+                        const double *col = tile + f;
+                        face_term<false>([col](int k) { return col[k * kSoaTileFaces]; }, Px, Py, Pz, ax, ay, az, pv);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars[kK2Stages + s]);
+            }
+        } else {
+            const int Fp = a.Fpad32;
+#pragma unroll 2
+            for (int f = lane; f < Fp; f += 32) {
+                const double *col = mesh + f;
+                face_term<false>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, ax, ay, az, pv);
+            }
+        }
+        if (!active) continue;
+        ax = warp_sum(ax);
+        ay = warp_sum(ay);
+        az = warp_sum(az);
+        ++n_rhs;
+        // k_stage = [ys[3..5], -g_pkg]   (equations_of_motion.py:59,92-95)
+        double kc = 0.0;
+        if (lane < 3) kc = vsh;
+        else if (lane == 3) kc = -(a.Grho * ax);
+        else if (lane == 4) kc = -(a.Grho * ay);
+        else if (lane == 5) kc = -(a.Grho * az);
+        if (lane < 6) sk[6 * stage + lane] = kc;
+        __syncwarp();
+
+        // ------------------------------------------------ advance the state machine
+        if (stage == 0) {
+            // f0 at a segment start or at a freshly accepted state: this is a knot
+            if (nk >= a.knot_cap) {
+                status = 3;
+            } else {
+                const size_t kb = (size_t)traj * a.knot_cap + nk;
+                if (lane == 0) a.knots_t[kb] = t;
+                if (lane < 6) {
+                    a.knots_y[kb * 6 + lane] = sy[lane];
+                    a.knots_f[kb * 6 + lane] = kc;
+                }
+                ++nk;
+            }
+            if (after_accept) {
+                after_accept = 0;
+                ++steps;
+                if (steps > p.max_steps) status = 1;
+            }
+            if (status == 0 && !(t < tf)) {   // segment finished
+                ++seg;
+                if (seg >= nseg) {
+                    active = false;
+                } else {
+                    // compute_trajectory.py:134-136: velocity REPLACED by the manoeuvre's dv
+                    if (lane >= 3 && lane < 6) sy[lane] = sdv[3 * (seg - 1) + (lane - 3)];
+                    __syncwarp();
+                    if (lane == 0) a.seg_start[(size_t)traj * (a.n_man + 2) + seg] = nk;
+                    t = seg_t[seg];
+                    tf = seg_t[seg + 1];
+                    dt = p.initial_time_step;
+                    steps = 0;
+                    stage = 0;   // f0 of the new segment
+                    continue;
+                }
+            } else if (status == 0) {
+                clipped = 0;
+                if (add_(t, dt) > tf) {
+                    dt = sub_(tf, t);
+                    clipped = 1;
+                }
+                stage = 1;
+                continue;
+            }
+        } else if (stage < 12) {
+            ++stage;
+            continue;
+        } else {
+            // all 13 stages in: error estimate and desolver's controller (oracle integrate_segment)
+            double e = 0.0, tl = 0.0, dy = 0.0;
+            if (lane < 6) {
+                double s8 = 0.0, se = 0.0;
+                for (int j = 0; j < 13; ++j) {
+                    const double kj = sk[6 * j + lane];
+                    s8 = add_(s8, mul_(TOSS_RK_B8[j], kj));
+                    se = add_(se, mul_(TOSS_RK_E[j], kj));
+                }
+                dy = mul_(dt, s8);
+                e = fabs(mul_(dt, se));
+                tl = add_(add_(p.atol, mul_(p.rtol, fabs(sy[lane]))), mul_(p.rtol, fabs(s8)));
+                if (e != e) e = __longlong_as_double(0x7ff0000000000000LL);   // NaN must win the max
+                if (tl != tl) tl = __longlong_as_double(0x7ff0000000000000LL);
+            }
+            const double err = warp_max(e), tol = warp_max(tl);
+            if (isinf(err) || isinf(tol)) {
+                status = 2;
+            } else {
+                double corr = 1.0;
+                if (err != 0.0) corr = mul_(0.8, pow(__ddiv_rn(tol, err), 0.125));
+                const double newdt = (corr != 0.0) ? mul_(corr, dt) : dt;
+                if (err > tol) {
+                    ++n_rej;
+                    dt = newdt;
+                    clipped = 0;
+                    ++steps;
+                    if (steps > p.max_steps || !(dt > 0.0)) status = 1;
+                    else {
+                        stage = 1;
+                        continue;
+                    }
+                } else {
+                    t = clipped ? tf : add_(t, dt);
+                    if (lane < 6) sy[lane] = add_(sy[lane], dy);
+                    __syncwarp();
+                    dt = newdt;
+                    ++n_acc;
+                    after_accept = 1;
+                    stage = 0;
+                    continue;
+                }
+            }
+        }
+        // ------------------------------------------------ retire (finished or failed)
+        active = false;
+        if (lane == 0) {
+            a.seg_start[(size_t)traj * (a.n_man + 2) + (seg < nseg ? seg + 1 : nseg)] = nk;
+            if (status != 0) a.n_seg[traj] = seg < nseg ? seg + 1 : nseg;
+            toss_counters c;
+            c.n_rhs = n_rhs;
+            c.n_accepted = n_acc;
+            c.n_rejected = n_rej;
+            c.n_event_points = 0;
+            c.status = status;
+            a.counters[traj] = c;
+            a.collision[traj] = 0;
+        }
+    }
+
+    // drain the TMA copies still in flight before the CTA's shared memory goes away
+    if (kStream && tid == 0) {
+        for (uint32_t it = tile_it; it < issued; ++it) mbar_wait(&bars[it % kK2Stages], (it / kK2Stages) & 1u);
+    }
+}
+
+int toss_workspace_layout_impl(int pop, int n_man, int knot_cap, toss_ws_layout *out)
+{
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t o = 0;
+    out->knots_t = o;   o = up(o + sizeof(double) * (size_t)pop * knot_cap);
+    out->knots_y = o;   o = up(o + sizeof(double) * (size_t)pop * knot_cap * 6);
+    out->knots_f = o;   o = up(o + sizeof(double) * (size_t)pop * knot_cap * 6);
+    out->seg_start = o; o = up(o + sizeof(int32_t) * (size_t)pop * (n_man + 2));
+    out->intervals = o; o = up(o + sizeof(double) * (size_t)pop * (n_man + 2));
+    out->n_seg = o;     o = up(o + sizeof(int32_t) * (size_t)pop);
+    out->counters = o;  o = up(o + sizeof(toss_counters) * (size_t)pop);
+    out->collision = o; o = up(o + sizeof(int32_t) * (size_t)pop);
+    out->queue = o;     o = up(o + sizeof(int32_t) * 4);
+    out->total_bytes = o;
+    return 0;
+}
+
+int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
+                     int n_fixed, int n_man, void *d_ws, int knot_cap, cudaStream_t st)
+{
+    TOSS_REQUIRE(ctx && ctx->d_face_soa, "toss_propagate: no mesh uploaded");
+    TOSS_REQUIRE(pop > 0 && dim >= 0 && n_fixed >= 0 && n_fixed <= 7, "toss_propagate: bad population shape");
+    TOSS_REQUIRE(n_man >= 0 && n_man <= 64, "toss_propagate: number_of_maneuvers must be in [0, 64]");
+    TOSS_REQUIRE(n_fixed + dim == 7 + 5 * n_man, "toss_propagate: n_fixed + dim != 7 + 5*number_of_maneuvers");
+    TOSS_REQUIRE(knot_cap >= 4, "toss_propagate: knot capacity too small");
+    TOSS_REQUIRE((int32_t)p->final_time > (int32_t)p->start_time, "toss_propagate: final_time <= start_time");
+    toss_ws_layout L;
+    toss_workspace_layout_impl(pop, n_man, knot_cap, &L);
+    unsigned char *ws = static_cast<unsigned char *>(d_ws);
+    StepArgs a;
+    a.p = *p;
+    a.axis = unit_axis_host(p->spin_axis);
+    a.Grho = ctx->Grho;
+    a.face_soa = ctx->d_face_soa;
+    a.face_tiles = ctx->d_face_tiles;
+    a.Fpad32 = ctx->Fpad32;
+    a.n_tiles = ctx->n_soa_tiles;
+    a.x = d_x;
+    a.pop = pop;
+    a.dim = dim;
+    a.n_fixed = n_fixed;
+    a.n_man = n_man;
+    a.knot_cap = knot_cap;
+    for (int i = 0; i < 8; ++i) a.fixed[i] = (i < n_fixed && h_fixed) ? h_fixed[i] : 0.0;
+    a.knots_t = reinterpret_cast<double *>(ws + L.knots_t);
+    a.knots_y = reinterpret_cast<double *>(ws + L.knots_y);
+    a.knots_f = reinterpret_cast<double *>(ws + L.knots_f);
+    a.intervals = reinterpret_cast<double *>(ws + L.intervals);
+    a.seg_start = reinterpret_cast<int32_t *>(ws + L.seg_start);
+    a.n_seg = reinterpret_cast<int32_t *>(ws + L.n_seg);
+    a.collision = reinterpret_cast<int32_t *>(ws + L.collision);
+    a.queue = reinterpret_cast<int32_t *>(ws + L.queue);
+    a.counters = reinterpret_cast<toss_counters *>(ws + L.counters);
+    TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 16, st));
+
+    const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + 64;
+    const size_t resident_bytes = (size_t)kFaceFields * ctx->Fpad32 * 8 + state_bytes;
+    const size_t stream_bytes = (size_t)kK2Stages * kSoaTileBytes + state_bytes;
+    const bool resident = resident_bytes <= 100 * 1024;   // two CTAs per SM keep their own copy
+    int ctas = (pop + kK2Warps - 1) / kK2Warps;
+    const int max_ctas = 2 * ctx->sm_count;
+    if (ctas > max_ctas) ctas = max_ctas;
+    if (resident) {
+        TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)resident_bytes));
+        stepper_kernel<false><<<ctas, kK2Threads, resident_bytes, st>>>(a);
+    } else {
+        TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)stream_bytes));
+        stepper_kernel<true><<<ctas, kK2Threads, stream_bytes, st>>>(a);
+    }
+    ctx->launches++;
+    TOSS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
