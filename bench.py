@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- the TOSS population-fitness path on B200 (contract: README of the driver).
+
+A "step" is ONE evaluation of the whole hot path over one population:
+    chromosomes -> RK8(7)-13M trajectories through the polyhedral gravity field (K2) -> collision verdict (K5)
+    -> fixed-step Hermite resampling + covered-space / penalty fitness (K3+K4 fused) -> fitness all-gather.
+
+Workload (BASELINE.json configs[4], the scaling benchmark; configs[1] -- the 1 M-point gravity microbench on
+the same lp mesh -- is reported beside it in `gravity_microbench`): lp 67P mesh (1828 faces), 1 spacecraft,
+2 manoeuvres, 7-day window, default_cfg.toml tolerances, 6048 samples, 6x8x17 voxel grid; synthetic
+"init-like" chromosomes, 4096 per GPU (32768 on 8 GPUs), sharded as contiguous islands with no
+data-path collective except one all-gather of the fitness vector.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pop-per-gpu P] [--mesh lp]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W_FACE = 127            # algorithmic FP64 operations per face-point pair (each sqrt/div/log/atan = 1)
+FIXED_POS = np.array([-135.13402075, -4089.53592604, 6050.17636635])   # default_cfg.toml initial_x/y/z
+N_MAN = 2
+
+
+def init_like_population(pop: int, n_man: int, seed: int, final_time: float = 604800.0) -> np.ndarray:
+    """genes uniform in the cfg bounds (default_cfg.toml [chromosome], setup_state.py:32)."""
+    rng = np.random.default_rng(seed)
+    cols = [rng.uniform(0, 1, pop)] + [rng.uniform(-1, 1, pop) for _ in range(3)]
+    for _ in range(n_man):
+        cols += [rng.uniform(1, final_time - 1, pop), rng.uniform(0, 2.5, pop)]
+        cols += [rng.uniform(-1, 1, pop) for _ in range(3)]
+    return np.stack(cols, axis=1)
+
+
+def gravity_points(n: int, seed: int = 0) -> np.ndarray:
+    """configs[1]: directions ~ normalised N(0,1)^3, radius ~ U[4000, 12500] m."""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    return d * rng.uniform(4000.0, 12500.0, size=(n, 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU path for this hot path, on the host cores.  The reference's own
+    third-party binaries (polyhedral_gravity / desolver / pygmo) cannot be installed here (no network, not in
+    the wheelhouse: DESIGN.md), so this times the CPU oracle port -- the one place besides cpu_baseline where
+    bench.py may execute oracle/ -- with every host thread, each step a bounded sample of the same population."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    v, f = O.load_mesh(args.mesh)
+    mesh = O.Mesh(v, f)
+    p = O.default_params()
+    grid = O.default_grid()
+    pop_total = args.pop_per_gpu * args.gpus
+    xs = init_like_population(pop_total, N_MAN, 1005)
+    sample = min(pop_total, max(cores, args.ref_sample if args.ref_sample else 16 * cores))
+    for _ in range(args.warmup):
+        O.population_fitness(mesh, p, grid, xs[:min(sample, cores)], FIXED_POS, N_MAN, threads=cores)
+    t0 = time.perf_counter()
+    n_rhs = 0
+    for k in range(args.steps):
+        lo = (k * sample) % max(pop_total - sample + 1, 1)
+        r = O.population_fitness(mesh, p, grid, xs[lo:lo + sample], FIXED_POS, N_MAN, threads=cores)
+        n_rhs += int(r["counters"]["n_rhs"].sum())
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "candidate_trajectories_per_sec", "value": value, "unit": "trajectories/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, pop_total),
+        "gravity_evals_per_sec": n_rhs / dt,
+        "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of the {pop_total} chromosomes per step x {args.steps} steps "
+                                   f"(oracle/toss_oracle.c, {cores} pthreads; the reference's own binaries are not installable here)"},
+        "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, pop_total):
+    return {"workload": f"BASELINE configs[4]: population fitness, pop {pop_total} sharded as islands over {args.gpus} "
+                        f"B200 ({args.pop_per_gpu}/GPU), {args.mesh} 67P mesh, 1 spacecraft, {N_MAN} manoeuvres, 7-day window, "
+                        f"rtol=atol=1e-12, 6048 samples, covered-space + penalties + collision fitness (enum 9)",
+            "mesh": args.mesh, "population": pop_total, "pop_per_gpu": args.pop_per_gpu, "maneuvers": N_MAN,
+            "chromosomes": "init-like, seed 1005 (SURVEY.md 8d)", "parallelism": f"islands x{args.gpus}",
+            "l2": "256 MiB buffer overwritten between steps (inside the timed region; < 0.02 % of a step)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from toss_b200 import _native as N
+    from oracle import oracle as O          # mesh loader + the cpu_baseline leg ONLY
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = N.Context(local_rank)
+    v, f = O.load_mesh(args.mesh)
+    F = len(f)
+    ctx.upload_mesh(v, f, 533.0)
+    ctx.upload_grid(*O.default_grid())
+    p = N.make_params()
+    pop_total = args.pop_per_gpu * world
+    xs_all = init_like_population(pop_total, N_MAN, 1005)
+    lo, hi = rank * args.pop_per_gpu, (rank + 1) * args.pop_per_gpu
+    xs_host = torch.from_numpy(xs_all[lo:hi].copy()).pin_memory()
+    xs_dev = xs_host.cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    gathered = torch.empty(pop_total, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        """inputs resident in HBM: kernels + fitness all-gather + champion"""
+        flush.fill_(1)
+        res = ctx.population_fitness(p, xs_dev, FIXED_POS, N_MAN, args.knot_cap)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, res["fitness"])
+            champ = torch.argmin(gathered)
+        else:
+            champ = torch.argmin(res["fitness"])
+        return res, champ
+
+    # the user-facing call: the pygmo UDP's batch_fitness on HOST decision vectors (shards itself over the
+    # process group, copies its shard H2D from pinned memory, runs the kernels, copies the fitness D2H, all-gathers)
+    import toss_b200 as T
+    targs = T.setup_parameters()
+    mesh_file = {"lllp": "churyumov-gerasimenko_lllp", "llp": "churyumov-gerasimenko_llp",
+                 "lp": "churyumov-gerasimenko_lp", "full": "churyumov-gerasimenko"}[args.mesh]
+    targs.mesh.mesh_path = f"3dmeshes/{mesh_file}.pk"
+    (targs.mesh.body, targs.mesh.vertices, targs.mesh.faces,
+     targs.mesh.largest_body_protuberant) = T.create_mesh(targs.mesh.mesh_path)
+    lb, ub = T.setup_initial_state_domain(FIXED_POS, targs.problem.start_time, targs.problem.final_time, N_MAN,
+                                          targs.problem.number_of_spacecrafts, targs.chromosome)
+    udp = T.udp_initial_condition(targs, FIXED_POS, lb, ub)
+    udp.knot_capacity = args.knot_cap
+    dvs_host = xs_all.ravel().copy()
+
+    def step_e2e():
+        flush.fill_(1)
+        return udp.batch_fitness(dvs_host)
+
+    # ---- FP64 peak (roofline denominator), measured on this box
+    fp64_peak = ctx.measure_fp64_peak()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        res, champ = step_device()
+    torch.cuda.synchronize()
+    cnt = res["counters"].cpu().numpy().view(N.COUNTERS_DTYPE)
+    n_rhs_local = int(cnt["n_rhs"].sum())
+    status_bad = int((cnt["status"] != 0).sum())
+    collided = int(res["collision"].sum().item())
+
+    # ---- timed: K steps, device-resident inputs
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        res, champ = step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed: K steps end to end (host buffers)
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_match = bool(np.array_equal(out[lo:hi], res["fitness"].cpu().numpy()))
+
+    # ---- the dominant kernel alone (stepper), CUDA events on the launching stream
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ctx.integrate(p, xs_dev, FIXED_POS, N_MAN, args.knot_cap)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(args.steps):
+        ctx.integrate(p, xs_dev, FIXED_POS, N_MAN, args.knot_cap)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+
+    # ---- max over ranks / totals
+    t = torch.tensor([ms, e2e_s * 1e3, kernel_ms, float(n_rhs_local), float(status_bad), float(collided)],
+                     dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    else:
+        tmax, tsum = t, t
+    ms, e2e_ms, kernel_ms = float(tmax[0]), float(tmax[1]), float(tmax[2])
+    n_rhs_total, status_bad, collided = float(tsum[3]), int(tsum[4]), int(tsum[5])
+
+    if rank == 0:
+        value = pop_total * args.steps / (ms * 1e-3)
+        alg_flops_per_launch = n_rhs_local * float(F) * W_FACE            # this rank's stepper launch
+        achieved = alg_flops_per_launch / (kernel_ms * 1e-3) / 1e12
+        line = {
+            "metric": "candidate_trajectories_per_sec", "value": value, "unit": "trajectories/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, pop_total),
+            "gravity_evals_per_sec": n_rhs_total * args.steps / (ms * 1e-3),
+            "gravity_evals_per_trajectory": n_rhs_total / pop_total,
+            "trajectories_failed": status_bad, "trajectories_collided": collided,
+            "e2e_equals_device_path": e2e_match,
+            "clocks": clocks,
+            "e2e": {"value": pop_total * args.steps / (e2e_ms * 1e-3), "unit": "trajectories/s",
+                    "h2d_bytes_per_step": int(xs_host.numel() * 8 * world),
+                    "d2h_bytes_per_step": int(pop_total * 8 * world),
+                    "api": "toss_b200.udp_initial_condition.batch_fitness(host decision vectors) -> host fitness vector"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "kernel": "stepper_kernel (K2: RK8(7)-13M + polyhedral gravity)",
+                         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         "peak_source": "measured live: register-resident DFMA chains on all SMs (toss_measure_fp64_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "algorithmic_flops_per_launch": alg_flops_per_launch, "kernel_ms": kernel_ms,
+                         "traffic": None,
+                         "note": f"algorithmic = gravity evaluations x {F} faces x {W_FACE} ops (SURVEY.md 8d)"},
+        }
+        if not args.no_microbench:
+            line["gravity_microbench"] = gravity_microbench(ctx, F, fp64_peak)
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(O, args, xs_all)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def gravity_microbench(ctx, F, fp64_peak):
+    """BASELINE configs[1]: 1 M random field points on the mesh, FP64, K1 kernel alone."""
+    import torch
+    pts = torch.from_numpy(gravity_points(1_000_000, 0)).cuda()
+    for _ in range(3):
+        ctx.gravity(pts)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        ctx.gravity(pts)
+    e1.record()
+    torch.cuda.synchronize()
+    s = e0.elapsed_time(e1) * 1e-3 / reps
+    ach = 1e6 * F * W_FACE / s / 1e12
+    return {"workload": "BASELINE configs[1]: 1 M random field points, FP64", "gravity_evals_per_sec": 1e6 / s,
+            "ms": s * 1e3, "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                                        "frac": ach / fp64_peak}}
+
+
+def cpu_baseline(O, args, xs_all):
+    """The CPU oracle port on the box's host cores, bounded sample of the same population (rank 0, N=1 only
+    matters; reported, not the optimisation target)."""
+    cores = os.cpu_count() or 1
+    v, f = O.load_mesh(args.mesh)
+    mesh = O.Mesh(v, f)
+    sample = min(len(xs_all), 40 * cores)      # ~15-25 s of host work on the lp mesh
+    t0 = time.perf_counter()
+    r = O.population_fitness(mesh, O.default_params(), O.default_grid(), xs_all[:sample], FIXED_POS, N_MAN, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "trajectories/s", "cores": cores, "kind": "port",
+            "gravity_evals_per_sec": float(r["counters"]["n_rhs"].sum()) / dt,
+            "sample": f"first {sample} chromosomes of the same population, oracle/toss_oracle.c on {cores} pthreads, {dt:.1f} s"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pop-per-gpu", type=int, default=4096)
+    ap.add_argument("--mesh", default="lp", choices=["lllp", "llp", "lp", "full"])
+    ap.add_argument("--knot-cap", type=int, default=2048)
+    ap.add_argument("--ref-sample", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-microbench", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,11 @@ int toss_gravity_eval(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_a
 int toss_compute_motion(toss_ctx *ctx, const toss_params *p, const double *d_t, const double *d_y, int64_t n,
                         double *d_out, uintptr_t stream);
 
+/* Replaces rotate_point(t, x, spin_axis, spin_velocity) (equations_of_motion.py:98-117, pyquaternion
+ * Quaternion(axis, angle = -w t).rotate) for n points: d_t (n), d_x n x 3 -> d_out n x 3. */
+int toss_rotate_points(toss_ctx *ctx, const double *h_axis3, double spin_velocity, const double *d_t,
+                       const double *d_x, int64_t n, double *d_out, uintptr_t stream);
+
 /* workspace for toss_propagate: the caller allocates total_bytes of device memory */
 int toss_workspace_layout(int pop, int n_man, int knot_cap, toss_ws_layout *out);
 
@@ -114,6 +119,14 @@ int toss_workspace_layout(int pop, int n_man, int knot_cap, toss_ws_layout *out)
 int toss_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim,
                    const double *h_fixed, int n_fixed, int n_man, void *d_workspace, int knot_cap,
                    uintptr_t stream);
+
+/* The two halves of toss_propagate, separately launchable (bench.py times the first alone):
+ * toss_integrate = the stepper (desolver OdeSystem.integrate for every segment, compute_trajectory.py:130-148);
+ * toss_collision_verdict = is_outside over the recorded event points (compute_trajectory.py:154-159). */
+int toss_integrate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
+                   int n_fixed, int n_man, void *d_workspace, int knot_cap, uintptr_t stream);
+int toss_collision_verdict(toss_ctx *ctx, const toss_params *p, void *d_workspace, int pop, int n_man, int knot_cap,
+                           uintptr_t stream);
 
 /* Replaces get_trajectory_fixed_step(args, list_of_ode_objects) (trajectory_tools.py:28-76) for the
  * trajectories in the workspace: d_pos / d_vel are pop x 3 x N (N = toss_num_samples), d_ts is N. */

@@ -1,0 +1,176 @@
+"""CPU tests of the host side: config contract, chromosome bounds, sharding + gather over a 2-rank gloo group,
+the C-ABI library loads and exports every symbol include/toss_b200.h declares (no compute without a GPU)."""
+import copy
+import os
+import pickle
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from toss_b200 import _native as N
+    lib = N.lib()
+    header = (ROOT / "include" / "toss_b200.h").read_text()
+    declared = set(re.findall(r"\b(toss_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes found"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/toss_b200.h but not exported"
+    assert declared == set(N.EXPORTS)
+    assert lib.toss_version().decode().startswith("toss_b200")
+
+
+def test_struct_layouts_match_the_header():
+    import ctypes as C
+    from toss_b200 import _native as N
+    from oracle import oracle as O
+    assert C.sizeof(N.TossParams) == C.sizeof(O.OrcParams) == 160
+    assert N.COUNTERS_DTYPE.itemsize == 24
+    L = N.WsLayout()
+    assert N.lib().toss_workspace_layout(10, 2, 64, C.byref(L)) == 0
+    assert L.knots_y - L.knots_t >= 10 * 64 * 8 and L.total_bytes > L.queue
+    assert N.lib().toss_workspace_layout(0, 2, 64, C.byref(L)) != 0
+    assert b"bad argument" in N.lib().toss_last_error()
+
+
+def test_no_gpu_means_a_loud_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from toss_b200 import _native as N
+    with pytest.raises(N.TossError):
+        N.Context(0)
+    import toss_b200 as T
+    args = T.setup_parameters()
+    with pytest.raises(N.TossError):
+        T.compute_motion(0.0, np.zeros(6) + 5000.0, args)
+
+
+def test_product_never_imports_the_oracle():
+    for f in (ROOT / "toss_b200").rglob("*"):
+        if f.suffix in (".py", ".cu", ".cuh", ".h") and f.is_file():
+            txt = f.read_text()
+            assert "oracle" not in txt.replace("oracle_parameter", ""), f"{f} mentions the oracle"
+
+
+def test_default_cfg_contract():
+    import toss_b200 as T
+    a = T.load_default_cfg()
+    for sec in ("body", "integrator", "problem", "optimization", "chromosome", "algorithm", "mesh"):
+        assert sec in a
+    assert a.integrator.algorithm == 3 and a.integrator.rtol == 1e-12
+    assert a.problem.final_time == 604800 and a.problem.number_of_spacecrafts == 4
+    with pytest.raises(AttributeError):
+        a.problem.no_such_key            # DotMap(_dynamic=False) semantics
+    a.problem.new_key = 3
+    assert a.problem.new_key == 3
+    b = copy.deepcopy(a)
+    b.problem.final_time = 1
+    assert a.problem.final_time == 604800
+    assert pickle.loads(pickle.dumps(a)).body.density == 533
+
+
+def test_setup_parameters_derived_fields():
+    import toss_b200 as T
+    from math import pi
+    a = T.setup_parameters()
+    assert a.mesh.vertices.shape == (93, 3) and a.mesh.faces.shape == (182, 3)
+    assert np.isclose(a.body.spin_velocity, 2 * pi / 43416)
+    assert np.array_equal(a.body.spin_axis, [0, 0, 1])
+    assert np.isclose(a.problem.total_measurable_volume, 4 / 3 * pi * (12500 ** 3 - 4000 ** 3))
+    assert a.problem.bool_tensor.shape == (6, 8, 17) and not a.problem.bool_tensor.any()
+    assert np.isclose(a.problem.tensor_grid_r[1] - a.problem.tensor_grid_r[0], 1700.0)
+    assert 3000 < a.mesh.largest_body_protuberant < 4000
+
+
+def test_spin_axis_goldens():
+    """reference tests/point_rotation_test.py:78-103"""
+    import toss_b200 as T
+    from toss_b200.utilities.dotmap import DotMap
+    from tests.golden import reference_goldens as G
+    for (dec, ra), axis in G.SPIN_AXIS_CASES:
+        a = DotMap(body=DotMap(declination=dec, right_ascension=ra, _dynamic=False), _dynamic=False)
+        assert np.allclose(T.setup_spin_axis(a), axis, rtol=1e-5, atol=1e-5)
+
+
+def test_chromosome_bounds_layouts():
+    """setup_state.py:35-47: dim = 7+5M, 4+5M, 5M"""
+    import toss_b200 as T
+    a = T.load_default_cfg()
+    for fixed, dim in ((np.zeros(0), 17), (np.zeros(3), 14), (np.zeros(7), 10)):
+        lb, ub = T.setup_initial_state_domain(fixed, 0, 604800, 2, 4, a.chromosome)
+        assert len(lb) == len(ub) == dim
+        assert lb[-5] == 1 and ub[-5] == 604799 and ub[-4] == 2.5
+
+
+def test_udp_is_picklable_and_validates_shapes():
+    import toss_b200 as T
+    a = T.setup_parameters()
+    fixed = np.array([a.problem.initial_x, a.problem.initial_y, a.problem.initial_z])
+    lb, ub = T.setup_initial_state_domain(fixed, a.problem.start_time, a.problem.final_time,
+                                          a.problem.number_of_maneuvers, a.problem.number_of_spacecrafts, a.chromosome)
+    udp = T.udp_initial_condition(a, fixed, lb, ub)
+    assert udp.args.problem.number_of_spacecraft == 1 and udp.get_nobj() == 1
+    assert np.array_equal(udp.get_bounds()[0], lb)
+    u2 = pickle.loads(pickle.dumps(copy.deepcopy(udp)))
+    assert np.array_equal(u2.get_bounds()[1], ub) and u2.args.mesh.faces.shape == (182, 3)
+    with pytest.raises(ValueError):
+        udp.batch_fitness(np.zeros(15))          # not a multiple of dim = 14
+    a.problem.radius_inner_bounding_sphere = 100.0
+    with pytest.raises(AssertionError):
+        T.udp_initial_condition(a, fixed, lb, ub)
+
+
+def test_shard_bounds_cover_the_population():
+    from toss_b200.parallel import shard_bounds, champion
+    for n in (0, 1, 7, 16, 32768, 33001):
+        for w in (1, 2, 3, 8):
+            cuts = [shard_bounds(n, r, w) for r in range(w)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
+            assert sizes == [len(c) for c in np.array_split(np.arange(n), w)]
+    assert champion(np.array([3.0, 1.0, 1.0, 2.0])) == (1, 1.0)
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from toss_b200.parallel import shard_bounds, gather_population_fitness, champion, world
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+n = 11
+truth = np.random.default_rng(4).normal(size=n)
+lo, hi = shard_bounds(n)
+assert world() == (int(sys.argv[3]), 2)
+full = gather_population_fitness(truth[lo:hi].copy(), n)
+assert np.array_equal(full, truth), (full, truth)
+assert champion(full) == (int(np.argmin(truth)), float(truth.min()))
+# a rank with an empty shard (n < world) still takes part in the collective
+one = gather_population_fitness(truth[:1] if dist.get_rank() == 0 else None, 1)
+assert one.shape == (1,) and one[0] == truth[0]
+dist.barrier(); dist.destroy_process_group()
+print("ok", lo, hi)
+'''
+
+
+def test_gather_over_two_gloo_ranks(tmp_path):
+    """islands = contiguous slices, one all-gather of the fitness vector (gloo stands in for NCCL)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(ROOT), port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert outs[0].strip().endswith("ok 0 6") and outs[1].strip().endswith("ok 6 11")

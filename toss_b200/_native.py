@@ -56,7 +56,7 @@ COUNTERS_DTYPE = np.dtype(
 EXPORTS = [
     "toss_version", "toss_last_error", "toss_ctx_create", "toss_ctx_destroy", "toss_mesh_upload",
     "toss_mesh_num_faces", "toss_grid_upload", "toss_gravity_eval", "toss_compute_motion",
-    "toss_workspace_layout", "toss_propagate", "toss_num_samples", "toss_resample", "toss_dense_eval",
+    "toss_rotate_points", "toss_workspace_layout", "toss_propagate", "toss_integrate", "toss_collision_verdict", "toss_num_samples", "toss_resample", "toss_dense_eval",
     "toss_fitness_eval", "toss_update_tensor", "toss_is_outside", "toss_population_fitness",
     "toss_population_fitness_host", "toss_measure_fp64_peak", "toss_launch_count",
 ]
@@ -99,6 +99,9 @@ def lib():
     L.toss_compute_motion.argtypes = [vp, pp, vp, vp, i64, vp, up]
     L.toss_workspace_layout.argtypes = [i32, i32, i32, C.POINTER(WsLayout)]
     L.toss_propagate.argtypes = [vp, pp, vp, i32, i32, c_double_p, i32, i32, vp, i32, up]
+    L.toss_integrate.argtypes = [vp, pp, vp, i32, i32, c_double_p, i32, i32, vp, i32, up]
+    L.toss_collision_verdict.argtypes = [vp, pp, vp, i32, i32, i32, up]
+    L.toss_rotate_points.argtypes = [vp, c_double_p, dbl, vp, vp, i64, vp, up]
     L.toss_num_samples.restype = i64
     L.toss_num_samples.argtypes = [pp]
     L.toss_resample.argtypes = [vp, pp, vp, i32, i32, i32, vp, vp, vp, up]
@@ -245,6 +248,16 @@ class Context:
                                          out.data_ptr(), self._stream()))
         return out
 
+    def rotate_points(self, axis, spin_velocity, ts, xs):
+        t = self.torch
+        ts = self._dev(ts).reshape(-1)
+        xs = self._dev(xs).reshape(-1, 3)
+        out = t.empty_like(xs)
+        axis = _f64(axis)
+        _check(lib().toss_rotate_points(self.h, _dp(axis), float(spin_velocity), ts.data_ptr(), xs.data_ptr(), len(xs),
+                                        out.data_ptr(), self._stream()))
+        return out
+
     def is_outside(self, points):
         t = self.torch
         pts = self._dev(points).reshape(-1, 3)
@@ -269,6 +282,17 @@ class Context:
         fixed = _f64(fixed)
         ws, L = self.workspace(pop, n_man, knot_cap)
         _check(lib().toss_propagate(self.h, C.byref(params), xs.data_ptr(), pop, dim,
+                                    _dp(fixed) if len(fixed) else None, len(fixed), n_man, ws.data_ptr(), knot_cap,
+                                    self._stream()))
+        return PropagationResult(self, ws, L, pop, n_man, knot_cap)
+
+    def integrate(self, params: TossParams, xs, fixed, n_man: int, knot_cap: int = 4096):
+        """the stepper kernel alone (no collision verdict): what bench.py times for the roofline"""
+        xs = self._dev(xs)
+        pop, dim = xs.shape
+        fixed = _f64(fixed)
+        ws, L = self.workspace(pop, n_man, knot_cap)
+        _check(lib().toss_integrate(self.h, C.byref(params), xs.data_ptr(), pop, dim,
                                     _dp(fixed) if len(fixed) else None, len(fixed), n_man, ws.data_ptr(), knot_cap,
                                     self._stream()))
         return PropagationResult(self, ws, L, pop, n_man, knot_cap)

@@ -218,6 +218,30 @@ int toss_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int p
     return launch_collision(ctx, p, d_workspace, pop, n_man, knot_cap, (cudaStream_t)stream);
 }
 
+int toss_integrate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
+                   int n_fixed, int n_man, void *d_workspace, int knot_cap, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && p && d_workspace && (d_x || dim == 0), "toss_integrate: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_propagate(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_workspace, knot_cap, (cudaStream_t)stream);
+}
+
+int toss_collision_verdict(toss_ctx *ctx, const toss_params *p, void *d_workspace, int pop, int n_man, int knot_cap,
+                           uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && p && d_workspace, "toss_collision_verdict: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_collision(ctx, p, d_workspace, pop, n_man, knot_cap, (cudaStream_t)stream);
+}
+
+int toss_rotate_points(toss_ctx *ctx, const double *h_axis3, double spin_velocity, const double *d_t,
+                       const double *d_x, int64_t n, double *d_out, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && h_axis3 && (n == 0 || (d_t && d_x && d_out)), "toss_rotate_points: NULL argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_rotate_points(ctx, h_axis3, spin_velocity, d_t, d_x, n, d_out, (cudaStream_t)stream);
+}
+
 int64_t toss_num_samples(const toss_params *p)
 {   // len(np.arange(start, final, period))  (trajectory_tools.py:46)
     const double n = ceil((p->final_time - p->start_time) / p->measurement_period);

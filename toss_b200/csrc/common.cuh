@@ -71,7 +71,7 @@ void toss_set_error(const std::string &msg);
 // ------------------------------------------------------------------------------------------------
 // un-contracted IEEE arithmetic: nvcc fuses a*b+c into FMA by default; wherever an INTEGER decision
 // (ray parity, voxel index, step accept/reject, sample->interval) hangs on the value we spell the
-// roundings out so they are the ones numpy / the -ffp-contract=off oracle perform.
+// roundings out so they are the ones numpy (un-fused, left to right) performs.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
@@ -139,3 +139,5 @@ int launch_fitness_knots(toss_ctx *ctx, const toss_params *p, const void *d_ws, 
                          double *d_fit, int32_t *d_coll, toss_counters *d_cnt, int64_t *d_nvis, cudaStream_t st);
 int launch_is_outside(toss_ctx *ctx, const double *d_pts, int64_t n, uint8_t *d_out, cudaStream_t st);
 int launch_fp64_peak(toss_ctx *ctx, double *tflops);
+int launch_rotate_points(toss_ctx *ctx, const double *h_axis3, double w, const double *d_t, const double *d_x,
+                         int64_t n, double *d_out, cudaStream_t st);

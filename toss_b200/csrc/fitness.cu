@@ -19,7 +19,7 @@ constexpr double kPi = 3.14159265358979323846;
 int toss_workspace_layout_impl(int pop, int n_man, int knot_cap, toss_ws_layout *out);
 
 // ---------------------------------------------------------------------------------------------
-// dense output: desolver's cubic Hermite between consecutive accepted steps (oracle hermite()).
+// dense output: desolver's cubic Hermite between consecutive accepted steps.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int bisect_knots(const double *__restrict__ kt, int n, double t)
 {

@@ -5,7 +5,7 @@
 //     S_p   = sum_q hq_s * LN_pq  +  hp * (sum_q sigma_pq AN_pq + singA_p)
 //     g_pkg = G rho sum_p N_p S_p            (package sign; TOSS uses -g_pkg)
 // with the two transcendental groups in their cancellation-free closed forms (same values; the literal
-// forms lose ~(l1+l2)/|G| ulps -- oracle/toss_oracle.c gravity_point vs gravity_point_direct):
+// forms lose ~(l1+l2)/|G| ulps to cancellation):
 //     LN_pq = ln((s2+l2)/(s1+l1)) = 2 atanh(|G_pq| / (l1 + l2))
 //     hp (sum_q sigma_pq AN_pq + singA_p) = -hp_s * omega_p,
 //     omega_p = 2 atan2(r0.(r1 x r2), l0 l1 l2 + l0 (r1.r2) + l1 (r2.r0) + l2 (r0.r1))

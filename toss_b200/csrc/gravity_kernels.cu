@@ -140,6 +140,19 @@ __global__ void __launch_bounds__(256) compute_motion_kernel(const double *__res
     }
 }
 
+// equations_of_motion.py:98-117 for a batch
+__global__ void rotate_points_kernel(UnitAxis k, double w, const double *__restrict__ ts, const double *__restrict__ xs,
+                                     int64_t n, double *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ox, oy, oz;
+    rotate_point_dev(ts[i], xs[3 * i], xs[3 * i + 1], xs[3 * i + 2], k.x, k.y, k.z, w, ox, oy, oz);
+    out[3 * i] = ox;
+    out[3 * i + 1] = oy;
+    out[3 * i + 2] = oz;
+}
+
 // K5 standalone: mesh_utility.py:70-89.  Warp per point, lanes stride the faces, integer hit count.
 __global__ void __launch_bounds__(256) is_outside_kernel(const double *__restrict__ soa, int Fpad32,
                                                          const double *__restrict__ pts, int64_t n,
@@ -233,6 +246,16 @@ int launch_is_outside(toss_ctx *ctx, const double *d_pts, int64_t n, uint8_t *d_
     if (n <= 0) return 0;
     const int64_t blocks = (n * 32 + 255) / 256;
     is_outside_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_face_soa, ctx->Fpad32, d_pts, n, d_out);
+    ctx->launches++;
+    TOSS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_rotate_points(toss_ctx *ctx, const double *h_axis3, double w, const double *d_t, const double *d_x,
+                         int64_t n, double *d_out, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    rotate_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(unit_axis_host(h_axis3), w, d_t, d_x, n, d_out);
     ctx->launches++;
     TOSS_CHECK_CUDA(cudaGetLastError());
     return 0;

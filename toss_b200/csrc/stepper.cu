@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a
             ++stage;
             continue;
         } else {
-            // all 13 stages in: error estimate and desolver's controller (oracle integrate_segment)
+            // all 13 stages in: error estimate and desolver's controller:
+            // err = max |h sum (b8-b7) k|, tol = max(atol + rtol |y| + rtol |dy/h|), h' = 0.8 h (tol/err)^(1/8)
             double e = 0.0, tl = 0.0, dy = 0.0;
             if (lane < 6) {
                 double s8 = 0.0, se = 0.0;

@@ -1,0 +1,93 @@
+"""udp_initial_condition -- the pygmo user-defined problem of toss/optimization/udp_initial_condition.py:13-147,
+with the new `batch_fitness`.
+
+`fitness(x)` keeps the reference's contract (one chromosome -> [float]); `batch_fitness(dvs)` follows pygmo's
+batch protocol (1-D array of n*dim concatenated decision vectors -> 1-D array of n fitness values), so
+`pg.bfe(pg.member_bfe())` / `pg.default_bfe()` route a whole generation to ONE call of the B200 path:
+propagate -> collision verdict -> fused resample + fitness, population sharded over ranks when a
+torch.distributed process group is active.  The object holds no device handles: pygmo may deep-copy and pickle it.
+"""
+from typing import Union
+
+import numpy as np
+
+from .._runtime import context_for_args, params_from_args
+from ..parallel import gather_population_fitness, shard_bounds
+
+
+class udp_initial_condition:
+
+    def __init__(self, args, initial_condition, lower_bounds, upper_bounds):
+        """Same assertions as the reference (:80-96), same attributes (:99-103)."""
+        self.target_sq_alt = args.problem.target_squared_altitude
+        assert self.target_sq_alt > 0
+        assert all(np.greater(upper_bounds, lower_bounds))
+        assert args.body.mu > 0
+        assert args.problem.final_time > args.problem.start_time
+        assert args.problem.initial_time_step <= args.problem.final_time - args.problem.start_time
+        assert args.problem.radius_inner_bounding_sphere > args.mesh.largest_body_protuberant
+        assert args.body.density > 0
+        assert args.body.declination >= 0
+        assert args.body.right_ascension >= 0
+        assert args.body.spin_period >= 0
+        assert args.problem.number_of_maneuvers >= 0
+        assert isinstance(args.problem.number_of_maneuvers, int)
+        assert isinstance(args.problem.activate_event, bool)
+        assert args.problem.radius_outer_bounding_sphere > args.problem.radius_inner_bounding_sphere
+        assert args.problem.squared_volume_outer_bounding_sphere > args.problem.squared_volume_inner_bounding_sphere
+        assert args.problem.total_measurable_volume > 0
+        assert args.problem.measurement_period > 0
+
+        self.args = args
+        self.initial_condition = initial_condition
+        self.lower_bounds = lower_bounds
+        self.upper_bounds = upper_bounds
+        self.args.problem.number_of_spacecraft = 1   # (sic) the reference sets this unused singular key (:103)
+        self.knot_capacity = 4096
+        self.last_batch = None                       # counters / collision flags of the latest batch
+
+    # ------------------------------------------------------------------------------------------
+    def get_bounds(self) -> Union[np.ndarray, np.ndarray]:
+        return (self.lower_bounds, self.upper_bounds)
+
+    def get_nobj(self) -> int:
+        return 1
+
+    def fitness(self, chromosome: np.ndarray) -> list:
+        """One chromosome -> [fitness] (1e30 when a collision is detected, :126-128): a batch of one."""
+        x = np.asarray(chromosome, dtype=np.float64).reshape(1, -1)
+        return [float(self._evaluate(x)[0])]
+
+    def batch_fitness(self, dvs: np.ndarray) -> np.ndarray:
+        """pygmo batch protocol: dvs holds n decision vectors back to back; returns n fitness values."""
+        dvs = np.asarray(dvs, dtype=np.float64)
+        dim = len(self.lower_bounds)
+        if dvs.ndim == 1:
+            if dvs.size % dim != 0:
+                raise ValueError(f"batch_fitness: {dvs.size} values is not a multiple of the problem dimension {dim}")
+            dvs = dvs.reshape(-1, dim)
+        return self._evaluate(dvs)
+
+    # ------------------------------------------------------------------------------------------
+    def _evaluate(self, xs: np.ndarray) -> np.ndarray:
+        args = self.args
+        n_man = int(args.problem.number_of_maneuvers)
+        fixed = np.asarray(self.initial_condition, dtype=np.float64).reshape(-1)
+        if fixed.size + xs.shape[1] != 7 + 5 * n_man:
+            raise ValueError(f"len(initial_condition) + len(chromosome) = {fixed.size + xs.shape[1]}, "
+                             f"expected 7 + 5*number_of_maneuvers = {7 + 5 * n_man}")
+        ctx = context_for_args(args, need_grid=True)
+        p = params_from_args(args)
+        lo, hi = shard_bounds(len(xs))
+        local = ctx.population_fitness_host(p, xs[lo:hi], fixed, n_man, self.knot_capacity) if hi > lo else None
+        if local is not None and (local["counters"]["status"] == 3).any():
+            raise RuntimeError("a trajectory needs more knots than udp.knot_capacity")
+        fit = gather_population_fitness(None if local is None else local["fitness"], len(xs), ctx)
+        self.last_batch = local
+        return fit
+
+    # pygmo deep-copies / pickles the UDP: nothing device-side lives on the object
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["last_batch"] = None
+        return d
