@@ -177,6 +177,14 @@ int toss_population_fitness_host(toss_ctx *ctx, const toss_params *p, const doub
  * the roofline denominator of bench.py (MEASURED_PEAKS.json has no FP64 entry). */
 int toss_measure_fp64_peak(toss_ctx *ctx, double *tflops_out);
 
+/* Test hooks of the arithmetic specification (toss_b200/csrc/tmath.cuh): evaluates elementary function `fn`
+ * (0 two_atanh, 1 log, 2 atan2(a,b), 3 sincos -> (out,out2), 4 x^(1/8), 5 x^(1/4), 6 8-term atan series,
+ * 7 a/b, 8 sqrt) over n device values; and counts, over `samples` pseudo-random operands, how often the
+ * guard-free division / square root differ from the IEEE-rounded intrinsics (must be 0). */
+int toss_math_probe(toss_ctx *ctx, int fn, const double *d_a, const double *d_b, int64_t n, double *d_out,
+                    double *d_out2, uintptr_t stream);
+int toss_selftest_div_sqrt(toss_ctx *ctx, int64_t samples, int64_t *bad_div, int64_t *bad_sqrt);
+
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 int64_t toss_launch_count(const toss_ctx *ctx);
 

@@ -62,8 +62,9 @@ COUNTERS_DTYPE = np.dtype(
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc only)."""
-    src = _HERE / "toss_oracle.c"
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    srcs = [_HERE / n for n in ("toss_oracle.c", "toss_oracle.h", "orc_math.h", "orc_math_constants.h",
+                                "rk8713m_tableau.h", "Makefile")]
+    if force or not _LIB_PATH.exists() or any(_LIB_PATH.stat().st_mtime < f.stat().st_mtime for f in srcs):
         subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
     return _LIB_PATH
 
@@ -81,6 +82,7 @@ def lib():
         L.orc_mesh_free.argtypes = [C.c_void_p]
         L.orc_gravity.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, C.c_int]
         L.orc_gravity_direct.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p]
+        L.orc_math_probe.argtypes = [C.c_int, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p]
         L.orc_rotate_point.argtypes = [C.c_double, c_double_p, c_double_p, C.c_double, c_double_p]
         L.orc_compute_motion.argtypes = [C.c_void_p, C.POINTER(OrcParams), C.c_double, c_double_p, c_double_p]
         L.orc_compute_trajectory.restype = C.c_int
@@ -219,6 +221,18 @@ def gravity_direct(mesh: Mesh, pts):
     acc = np.empty_like(pts)
     lib().orc_gravity_direct(mesh.handle, _dp(pts), len(pts), _dp(acc), None)
     return acc
+
+
+MATH_FN = dict(two_atanh=0, log=1, atan2=2, sincos=3, root8=4, root4=5, atan_series8=6, div=7, sqrt=8)
+
+
+def math_probe(fn: str, a, b=None):
+    """orc_math.h function `fn` over arrays (tests): returns out, or (sin, cos) for sincos."""
+    a = _f64(a).ravel()
+    b = _f64(b).ravel() if b is not None else np.zeros_like(a)
+    out, out2 = np.empty_like(a), np.empty_like(a)
+    lib().orc_math_probe(MATH_FN[fn], _dp(a), _dp(b), len(a), _dp(out), _dp(out2))
+    return (out, out2) if fn == "sincos" else out
 
 
 def rotate_point(t, x, axis, w):

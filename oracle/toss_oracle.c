@@ -4,6 +4,7 @@
  */
 #include "toss_oracle.h"
 #include "rk8713m_tableau.h"
+#include "orc_math.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -12,13 +13,13 @@
 #include <stdatomic.h>
 
 #define ORC_G 6.67430e-11 /* CODATA-2018, the value polyhedral_gravity >= 2.x uses */
-#define REC 33            /* doubles per face record */
+#define REC 34            /* doubles per face record */
 
 struct orc_mesh {
     int V, F;
     double *verts;
     int32_t *faces;
-    double *rec; /* per face: v0 v1 v2 | N | g0 g1 g2 | n0 n1 n2 | len0 len1 len2 */
+    double *rec; /* per face: v0 v1 v2 | N | g0 g1 g2 | n0 n1 n2 | len0 len1 len2 | 2*area */
     double Grho;
 };
 
@@ -95,6 +96,7 @@ orc_mesh *orc_mesh_create(const double *verts, int V, const int32_t *faces, int 
         double nn = norm3(N);
         for (int c = 0; c < 3; ++c) N[c] /= nn;
         memcpy(r + 9, N, 3 * sizeof(double));
+        r[33] = nn; /* |G0 x G1| = 2 * area: r0.(r1 x r2) = (N.r0) * 2A */
         for (int q = 0; q < 3; ++q) {
             double len = norm3(Gq[q]);
             double nq[3];
@@ -179,39 +181,72 @@ static void gravity_point_direct(const orc_mesh *m, const double P[3], double ac
  * tests/test_oracle_gravity.py which checks both forms against a 50-digit mpmath evaluation.)
  * The direct form loses ~ (l1+l2)/|G| ulps in ln(ratio ~ 1) and in the difference of two O(1)
  * arctangents; this form keeps every term to a few ulp, so it is the one parity is anchored on. */
+/* One face.  Operation order = the arithmetic specification the CUDA kernels implement too
+ * (toss_b200/csrc/gravity.cuh face_term): un-fused except where ORC_FMA says so.
+ * Fast path (the face is seen under a small solid angle and every edge under a small angle): the four
+ * quotients share ONE division, atanh / atan are short odd series.  Otherwise: separate divisions,
+ * ln-based atanh, full-range atan2. */
+static inline void face_term(const double *rc, const double P[3], double *ax, double *ay, double *az, double *pv)
+{
+    const double r0x = rc[0] - P[0], r0y = rc[1] - P[1], r0z = rc[2] - P[2];
+    const double r1x = rc[3] - P[0], r1y = rc[4] - P[1], r1z = rc[5] - P[2];
+    const double r2x = rc[6] - P[0], r2y = rc[7] - P[1], r2z = rc[8] - P[2];
+    const double l0 = sqrt(ORC_FMA(r0z, r0z, ORC_FMA(r0y, r0y, r0x * r0x)));
+    const double l1 = sqrt(ORC_FMA(r1z, r1z, ORC_FMA(r1y, r1y, r1x * r1x)));
+    const double l2 = sqrt(ORC_FMA(r2z, r2z, ORC_FMA(r2y, r2y, r2x * r2x)));
+    const double *N = rc + 9, *n = rc + 21, *G = rc + 30;
+    const double hp = ORC_FMA(N[2], r0z, ORC_FMA(N[1], r0y, N[0] * r0x));
+    const double hq0 = ORC_FMA(n[2], r0z, ORC_FMA(n[1], r0y, n[0] * r0x));
+    const double hq1 = ORC_FMA(n[5], r1z, ORC_FMA(n[4], r1y, n[3] * r1x));
+    const double hq2 = ORC_FMA(n[8], r2z, ORC_FMA(n[7], r2y, n[6] * r2x));
+    const double A0 = l0 + l1, A1 = l1 + l2, A2 = l2 + l0;
+    const double d12 = ORC_FMA(r1z, r2z, ORC_FMA(r1y, r2y, r1x * r2x));
+    const double d20 = ORC_FMA(r2z, r0z, ORC_FMA(r2y, r0y, r2x * r0x));
+    const double d01 = ORC_FMA(r0z, r1z, ORC_FMA(r0y, r1y, r0x * r1x));
+    const double den = ORC_FMA(l2, d01, ORC_FMA(l1, d20, ORC_FMA(l0, d12, (l0 * l1) * l2)));
+    const double num = hp * rc[33];
+    double ln0, ln1, ln2, om;
+    int fast = (den > 0.0) && (fabs(num) <= 0.1 * den);
+    if (fast) {
+        const double P01 = A0 * A1, P2D = A2 * den;
+        const double inv = 1.0 / (P01 * P2D);
+        const double i01 = P2D * inv, i2D = P01 * inv;
+        const double z0 = (G[0] * A1) * i01, z1 = (G[1] * A0) * i01, z2 = (G[2] * den) * i2D;
+        const double q = (num * A2) * i2D;
+        fast = (z0 * z0 < 0.04) && (z1 * z1 < 0.04) && (z2 * z2 < 0.04);
+        if (fast) {
+            ln0 = orc_two_atanh_series(z0);
+            ln1 = orc_two_atanh_series(z1);
+            ln2 = orc_two_atanh_series(z2);
+            om = 2.0 * orc_atan_series(q, 8);
+        }
+    }
+    if (!fast) {
+        ln0 = orc_two_atanh(G[0] / A0);
+        ln1 = orc_two_atanh(G[1] / A1);
+        ln2 = orc_two_atanh(G[2] / A2);
+        om = 2.0 * orc_atan2(num, den);
+    }
+    const double S = ORC_FMA(-hp, om, ORC_FMA(hq2, ln2, ORC_FMA(hq1, ln1, hq0 * ln0)));
+    *ax = ORC_FMA(N[0], S, *ax);
+    *ay = ORC_FMA(N[1], S, *ay);
+    *az = ORC_FMA(N[2], S, *az);
+    *pv = ORC_FMA(hp, S, *pv);
+}
+
+/* Sum over faces in the order of a 32-lane warp: lane l accumulates faces l, l+32, ... in increasing
+ * order, then an xor-butterfly adds the 32 partial sums (polyhedral_gravity itself reduces with an
+ * unspecified parallel order, so any fixed order is as faithful as another). */
 static void gravity_point(const orc_mesh *m, const double P[3], double acc[3], double *pot)
 {
-    double ax = 0.0, ay = 0.0, az = 0.0, vv = 0.0;
-    for (int f = 0; f < m->F; ++f) {
-        const double *rc = m->rec + (size_t)f * REC;
-        const double *N = rc + 9;
-        double r[3][3], l[3];
-        for (int i = 0; i < 3; ++i) {
-            for (int c = 0; c < 3; ++c) r[i][c] = rc[3 * i + c] - P[c];
-            l[i] = norm3(r[i]);
-        }
-        double hp_s = dot3(N, r[0]);
-        double S = 0.0;
-        for (int q = 0; q < 3; ++q) {
-            const double *n = rc + 21 + 3 * q;
-            double hq_s = dot3(n, r[q]);
-            double z = rc[30 + q] / (l[q] + l[(q + 1) % 3]);
-            S += hq_s * (2.0 * atanh(z));
-        }
-        double c12[3];
-        cross3(r[1], r[2], c12);
-        double num = dot3(r[0], c12);
-        double den = l[0] * l[1] * l[2] + l[0] * dot3(r[1], r[2]) + l[1] * dot3(r[2], r[0]) + l[2] * dot3(r[0], r[1]);
-        S -= hp_s * (2.0 * atan2(num, den));
-        ax += N[0] * S;
-        ay += N[1] * S;
-        az += N[2] * S;
-        vv += hp_s * S;
-    }
+    double sx[32] = {0.0}, sy[32] = {0.0}, sz[32] = {0.0}, sv[32] = {0.0};
+    for (int f = 0; f < m->F; ++f)
+        face_term(m->rec + (size_t)f * REC, P, &sx[f & 31], &sy[f & 31], &sz[f & 31], &sv[f & 31]);
+    const double ax = orc_butterfly32(sx), ay = orc_butterfly32(sy), az = orc_butterfly32(sz);
     acc[0] = m->Grho * ax;
     acc[1] = m->Grho * ay;
     acc[2] = m->Grho * az;
-    if (pot) *pot = 0.5 * m->Grho * vv;
+    if (pot) *pot = 0.5 * m->Grho * orc_butterfly32(sv);
 }
 
 void orc_gravity_direct(const orc_mesh *m, const double *pts, int64_t n, double *acc, double *pot)
@@ -242,7 +277,8 @@ void orc_rotate_point(double t, const double x[3], const double axis[3], double 
     double na = norm3(axis);
     double k[3] = {axis[0] / na, axis[1] / na, axis[2] / na};
     double th = -(w * t);
-    double c = cos(th), s = sin(th);
+    double c, s;
+    orc_sincos(th, &s, &c);
     double kx[3];
     cross3(k, x, kx);
     double kd = dot3(k, x) * (1.0 - c);
@@ -375,7 +411,7 @@ static int integrate_segment(const orc_mesh *m, const orc_params *p, double t0, 
                 if (tl > tol) tol = tl;
             }
             double corr = 1.0;
-            if (err != 0.0) corr = 0.8 * pow(tol / err, 1.0 / 8.0);
+            if (err != 0.0) corr = 0.8 * orc_root8(tol / err);
             newdt = (corr != 0.0) ? corr * dt : dt;
             if (!(err == err) || !(tol == tol)) { /* NaN */
                 cnt->status = 2;
@@ -570,8 +606,8 @@ void orc_fixed_step(const orc_params *p, const double *knots_t, const double *kn
 static void cart2sphere(const double *x, double *r, double *th, double *ph)
 {
     *r = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-    *th = atan2(x[2], sqrt(x[0] * x[0] + x[1] * x[1]));
-    *ph = atan2(x[1], x[0]);
+    *th = orc_atan2(x[2], sqrt(x[0] * x[0] + x[1] * x[1]));
+    *ph = orc_atan2(x[1], x[0]);
 }
 
 static int argmin_abs(const double *g, int n, double v)
@@ -668,12 +704,28 @@ static inline double sqdist(const double *pos, int64_t N, int64_t n, double c)
     return pos[n] * pos[n] + pos[N + n] * pos[N + n] + pos[2 * N + n] * pos[2 * N + n] - c * c;
 }
 
+/* reductions over samples run in the order of a 256-thread block (orc_block_sum256): numpy itself sums
+ * pairwise in blocks, so no particular order is "the reference's" -- this one is the GPU's. */
+typedef struct {
+    const double *pos;
+    int64_t N;
+    double c;
+    int mode; /* 0: |d|, 1: d where d > 0 else 0 */
+} sq_job;
+static double sq_item(int64_t n, void *v)
+{
+    const sq_job *j = (const sq_job *)v;
+    const double d = sqdist(j->pos, j->N, n, j->c);
+    if (j->mode == 0) return fabs(d);
+    return d > 0.0 ? d : 0.0;
+}
+
 /* fitness_functions.py:48-59 */
 static double target_altitude_distance(double tsa, const double *pos, int64_t N)
 {
-    double c = sqrt(tsa), s = 0.0;
-    for (int64_t n = 0; n < N; ++n) s += fabs(sqdist(pos, N, n, c));
-    return pow((s / (double)N) / tsa, 0.25);
+    sq_job j = {pos, N, sqrt(tsa), 0};
+    const double s = orc_block_sum256(N, sq_item, &j);
+    return orc_root4((s / (double)N) / tsa);
 }
 /* fitness_functions.py:62-85 */
 static double close_distance_penalty(double rin, const double *pos, int64_t N, double scale)
@@ -688,38 +740,41 @@ static double close_distance_penalty(double rin, const double *pos, int64_t N, d
         }
     }
     if (!any) return 0.0;
-    return pow(fabs(mn) / (rin * rin), 0.25) * scale;
+    return orc_root4(fabs(mn) / (rin * rin)) * scale;
 }
 /* fitness_functions.py:88-113 */
 static double far_distance_penalty(double rout, const double *pos, int64_t N, double scale)
 {
-    double s = 0.0;
     int64_t cnt = 0;
-    for (int64_t n = 0; n < N; ++n) {
-        double d = sqdist(pos, N, n, rout);
-        if (d > 0.0) {
-            s += d;
-            ++cnt;
-        }
-    }
+    for (int64_t n = 0; n < N; ++n) cnt += sqdist(pos, N, n, rout) > 0.0;
     if (!cnt) return 0.0;
-    return pow((s / (double)cnt) / (rout * rout), 0.25) * scale;
+    sq_job j = {pos, N, rout, 1};
+    const double s = orc_block_sum256(N, sq_item, &j);
+    return orc_root4((s / (double)cnt) / (rout * rout)) * scale;
 }
 /* fitness_function_utils.py:8-38 */
+typedef struct {
+    const double *pos;
+    int64_t N;
+} vol_job;
+static double vol_item(int64_t n, void *v)
+{
+    const vol_job *q = (const vol_job *)v;
+    const double *pos = q->pos;
+    const int64_t N = q->N;
+    /* radii[1:] = dist/2 ; radii[0] = radii[1] ; radii[-1] = radii[-2] */
+    int64_t j = n;
+    if (j == 0) j = 1;
+    if (n == N - 1) j = (N - 2 >= 1) ? N - 2 : 1;
+    double dx = pos[j] - pos[j - 1], dy = pos[N + j] - pos[N + j - 1], dz = pos[2 * N + j] - pos[2 * N + j - 1];
+    double rad = sqrt(dx * dx + dy * dy + dz * dz) / 2.0;
+    return (4.0 / 3.0) * M_PI * (rad * rad * rad);
+}
 static double estimate_covered_volume(const double *pos, int64_t N)
 {
     if (N < 2) return 0.0;
-    double s = 0.0;
-    for (int64_t n = 0; n < N; ++n) {
-        /* radii[1:] = dist/2 ; radii[0] = radii[1] ; radii[-1] = radii[-2] */
-        int64_t j = n;
-        if (j == 0) j = 1;
-        if (n == N - 1) j = (N - 2 >= 1) ? N - 2 : 1;
-        double dx = pos[j] - pos[j - 1], dy = pos[N + j] - pos[N + j - 1], dz = pos[2 * N + j] - pos[2 * N + j - 1];
-        double rad = sqrt(dx * dx + dy * dy + dz * dz) / 2.0;
-        s += (4.0 / 3.0) * M_PI * (rad * rad * rad);
-    }
-    return s;
+    vol_job j = {pos, N};
+    return orc_block_sum256(N, vol_item, &j);
 }
 
 double orc_get_fitness(int fn, const orc_params *p, const double *pos, int64_t N, const double *ts, const double *gr,
@@ -812,4 +867,25 @@ void orc_population_fitness(const orc_mesh *m, const orc_params *p, const double
     pop_job j = {m, p, gr, gth, gph, nr, nth, nph, bool_tensor, xs, fixed, dim, n_fixed, n_man,
                  fitness, collision, cnt, n_visited};
     parallel_for(pop, 1, threads, pop_body, &j);
+}
+
+/* elementary functions of orc_math.h, exposed for tests/test_oracle_math.py and the GPU bit-parity tests.
+ * fn: 0 two_atanh(a) 1 log(a) 2 atan2(a,b) 3 sincos(a)->(out,out2) 4 root8(a) 5 root4(a) 6 atan_series8(a)
+ *     7 a/b 8 sqrt(a) */
+void orc_math_probe(int fn, const double *a, const double *b, int64_t n, double *out, double *out2)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        switch (fn) {
+        case 0: out[i] = orc_two_atanh(a[i]); break;
+        case 1: out[i] = orc_log(a[i]); break;
+        case 2: out[i] = orc_atan2(a[i], b[i]); break;
+        case 3: orc_sincos(a[i], &out[i], &out2[i]); break;
+        case 4: out[i] = orc_root8(a[i]); break;
+        case 5: out[i] = orc_root4(a[i]); break;
+        case 6: out[i] = orc_atan_series(a[i], 8); break;
+        case 7: out[i] = a[i] / b[i]; break;
+        case 8: out[i] = sqrt(a[i]); break;
+        default: out[i] = NAN;
+        }
+    }
 }

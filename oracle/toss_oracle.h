@@ -126,6 +126,10 @@ void orc_population_fitness(const orc_mesh *m, const orc_params *p,
                             double *fitness, int32_t *collision, orc_counters *cnt, int64_t *n_visited,
                             int threads);
 
+/* orc_math.h functions by id (tests only): 0 two_atanh 1 log 2 atan2(a,b) 3 sincos 4 root8 5 root4
+ * 6 atan series (8 terms) 7 a/b 8 sqrt */
+void orc_math_probe(int fn, const double *a, const double *b, int64_t n, double *out, double *out2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,50 @@
+"""oracle/orc_math.h (explicit-IEEE-sequence elementary functions) against libm / numpy: they replace
+log / atan2 / sin / cos / pow in the oracle so that the GPU can match it bit for bit, and must themselves
+stay within a few ulp of the correctly rounded values.  CPU only."""
+import numpy as np
+
+from oracle import oracle as O
+
+
+def ulps(got, ref):
+    return np.abs(got - ref) / np.spacing(np.abs(ref))
+
+
+def test_two_atanh_and_log():
+    rng = np.random.default_rng(0)
+    z = np.concatenate([rng.uniform(0, 0.2, 200000), rng.uniform(0.2, 0.999, 200000), 10.0 ** rng.uniform(-8, -1, 50000)])
+    assert ulps(O.math_probe("two_atanh", z), 2 * np.arctanh(z)).max() <= 6
+    x = np.concatenate([rng.uniform(1.0, 4.0, 200000), 10.0 ** rng.uniform(-300, 300, 100000)])
+    got, ref = O.math_probe("log", x), np.log(x)
+    far = np.abs(ref) > 0.05
+    assert ulps(got[far], ref[far]).max() <= 3
+    assert np.abs(got - ref).max() / np.maximum(np.abs(ref), 0.05).min() < 1  # finite everywhere
+    assert np.abs(got[~far] - ref[~far]).max() < 4e-17
+
+
+def test_atan2_all_quadrants_and_small_series():
+    rng = np.random.default_rng(1)
+    y, x = rng.normal(size=400000) * 10.0 ** rng.uniform(-3, 6, 400000), rng.normal(size=400000) * 10.0 ** rng.uniform(-3, 6, 400000)
+    got, ref = O.math_probe("atan2", y, x), np.arctan2(y, x)
+    assert ulps(got, ref).max() <= 4
+    # axes and the branch cut
+    yy = np.array([0.0, 1.0, 0.0, -1.0, 1.0, -1.0, 0.0])
+    xx = np.array([1.0, 0.0, -1.0, 0.0, 1.0, -1.0, 0.0])
+    assert np.allclose(O.math_probe("atan2", yy, xx), np.arctan2(yy, xx), rtol=0, atol=3e-16)
+    q = rng.uniform(-0.1, 0.1, 200000)
+    assert ulps(O.math_probe("atan_series8", q), np.arctan(q)).max() <= 2
+
+
+def test_sincos():
+    rng = np.random.default_rng(2)
+    th = np.concatenate([rng.uniform(-100, 100, 400000), rng.uniform(-1e4, 1e4, 100000), [0.0, np.pi / 4, -np.pi / 2]])
+    s, c = O.math_probe("sincos", th)
+    assert np.abs(s - np.sin(th)).max() < 3e-16 and np.abs(c - np.cos(th)).max() < 3e-16
+    assert np.abs(s * s + c * c - 1).max() < 5e-16
+
+
+def test_roots():
+    rng = np.random.default_rng(3)
+    x = 10.0 ** rng.uniform(-30, 30, 200000)
+    assert ulps(O.math_probe("root8", x), x ** 0.125).max() <= 2
+    assert ulps(O.math_probe("root4", x), x ** 0.25).max() <= 2

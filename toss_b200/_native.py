@@ -58,7 +58,8 @@ EXPORTS = [
     "toss_mesh_num_faces", "toss_grid_upload", "toss_gravity_eval", "toss_compute_motion",
     "toss_rotate_points", "toss_workspace_layout", "toss_propagate", "toss_integrate", "toss_collision_verdict", "toss_num_samples", "toss_resample", "toss_dense_eval",
     "toss_fitness_eval", "toss_update_tensor", "toss_is_outside", "toss_population_fitness",
-    "toss_population_fitness_host", "toss_measure_fp64_peak", "toss_launch_count",
+    "toss_population_fitness_host", "toss_measure_fp64_peak", "toss_launch_count", "toss_math_probe",
+    "toss_selftest_div_sqrt",
 ]
 
 _lib = None
@@ -112,6 +113,8 @@ def lib():
     L.toss_population_fitness.argtypes = [vp, pp, vp, i32, i32, c_double_p, i32, i32, vp, i32, vp, vp, vp, vp, up]
     L.toss_population_fitness_host.argtypes = [vp, pp, c_double_p, i32, i32, c_double_p, i32, i32, i32,
                                                c_double_p, C.POINTER(C.c_int32), vp, C.POINTER(C.c_int64)]
+    L.toss_math_probe.argtypes = [vp, i32, vp, vp, i64, vp, vp, up]
+    L.toss_selftest_div_sqrt.argtypes = [vp, i64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.toss_measure_fp64_peak.argtypes = [vp, c_double_p]
     L.toss_launch_count.restype = i64
     L.toss_launch_count.argtypes = [vp]
@@ -375,6 +378,21 @@ class Context:
                                                   _dp(fit), coll.ctypes.data_as(C.POINTER(C.c_int32)), cnt.ctypes.data,
                                                   nv.ctypes.data_as(C.POINTER(C.c_int64))))
         return dict(fitness=fit, collision=coll, counters=cnt, n_visited=nv)
+
+    def math_probe(self, fn: int, a, b=None):
+        """tmath.cuh function `fn` over arrays (tests): numpy out, or (sin, cos) for fn 3"""
+        t = self.torch
+        a = self._dev(a).reshape(-1)
+        b = self._dev(b).reshape(-1) if b is not None else t.zeros_like(a)
+        out, out2 = t.empty_like(a), t.empty_like(a)
+        _check(lib().toss_math_probe(self.h, int(fn), a.data_ptr(), b.data_ptr(), len(a), out.data_ptr(),
+                                     out2.data_ptr(), self._stream()))
+        return (out.cpu().numpy(), out2.cpu().numpy()) if fn == 3 else out.cpu().numpy()
+
+    def selftest_div_sqrt(self, samples: int):
+        bd, bs = C.c_int64(), C.c_int64()
+        _check(lib().toss_selftest_div_sqrt(self.h, int(samples), C.byref(bd), C.byref(bs)))
+        return bd.value, bs.value
 
     def measure_fp64_peak(self) -> float:
         v = C.c_double()

@@ -384,6 +384,23 @@ int toss_population_fitness_host(toss_ctx *ctx, const toss_params *p, const doub
     return 0;
 }
 
+int toss_math_probe(toss_ctx *ctx, int fn, const double *d_a, const double *d_b, int64_t n, double *d_out,
+                    double *d_out2, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && (n == 0 || (d_a && d_out)), "toss_math_probe: NULL argument");
+    TOSS_REQUIRE(fn >= 0 && fn <= 8, "toss_math_probe: unknown function id");
+    TOSS_REQUIRE(!(fn == 2 || fn == 7) || d_b, "toss_math_probe: this function needs a second operand");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_math_probe(ctx, fn, d_a, d_b, n, d_out, d_out2, (cudaStream_t)stream);
+}
+
+int toss_selftest_div_sqrt(toss_ctx *ctx, int64_t samples, int64_t *bad_div, int64_t *bad_sqrt)
+{
+    TOSS_REQUIRE(ctx && bad_div && bad_sqrt && samples > 0, "toss_selftest_div_sqrt: bad argument");
+    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    return launch_div_sqrt_selftest(ctx, samples, bad_div, bad_sqrt);
+}
+
 int toss_measure_fp64_peak(toss_ctx *ctx, double *tflops_out)
 {
     TOSS_REQUIRE(ctx && tflops_out, "toss_measure_fp64_peak: NULL argument");

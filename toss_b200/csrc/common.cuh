@@ -6,6 +6,7 @@
 #include <string>
 
 #include "../../include/toss_b200.h"
+#include "tmath.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // face record: 25 doubles per face (SURVEY.md App. A.1 constants that do not depend on the field point)
@@ -101,7 +102,7 @@ __device__ __forceinline__ void rotate_point_dev(double t, double x, double y, d
 {
     double th = -mul_(w, t);
     double s, c;
-    sincos(th, &s, &c);
+    tm_sincos(th, s, c);
     double cx = sub_(mul_(ky, z), mul_(kz, y));
     double cy = sub_(mul_(kz, x), mul_(kx, z));
     double cz = sub_(mul_(kx, y), mul_(ky, x));
@@ -139,5 +140,8 @@ int launch_fitness_knots(toss_ctx *ctx, const toss_params *p, const void *d_ws, 
                          double *d_fit, int32_t *d_coll, toss_counters *d_cnt, int64_t *d_nvis, cudaStream_t st);
 int launch_is_outside(toss_ctx *ctx, const double *d_pts, int64_t n, uint8_t *d_out, cudaStream_t st);
 int launch_fp64_peak(toss_ctx *ctx, double *tflops);
+int launch_math_probe(toss_ctx *ctx, int fn, const double *a, const double *b, int64_t n, double *out, double *out2,
+                      cudaStream_t st);
+int launch_div_sqrt_selftest(toss_ctx *ctx, int64_t samples, int64_t *bad_div, int64_t *bad_sqrt);
 int launch_rotate_points(toss_ctx *ctx, const double *h_axis3, double w, const double *d_t, const double *d_x,
                          int64_t n, double *d_out, cudaStream_t st);

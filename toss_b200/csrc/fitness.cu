@@ -202,10 +202,10 @@ __device__ __forceinline__ void mark_voxel(uint32_t *bits, const GridArgs &g, co
     rotate_point_dev(t_clock, x, y, z, k.x, k.y, k.z, w, rx, ry, rz);
     // cart2sphere (fitness_function_utils.py:282-314)
     const double xy2 = add_(mul_(rx, rx), mul_(ry, ry));
-    const double r = sqrt(add_(xy2, mul_(rz, rz)));
+    const double r = __dsqrt_rn(add_(xy2, mul_(rz, rz)));
     if (!(r <= rmax) || !(r >= rmin)) return;   // :113-122 inclusive bounds
-    const double th = atan2(rz, sqrt(xy2));
-    const double ph = atan2(ry, rx);
+    const double th = tm_atan2(rz, __dsqrt_rn(xy2));
+    const double ph = tm_atan2(ry, rx);
     const int i = argmin_abs_dev(g.grid, g.nr, r);
     const int j = argmin_abs_dev(g.grid + g.nr, g.nth, th);
     const int kk = argmin_abs_dev(g.grid + g.nr + g.nth, g.nph, ph);
@@ -308,11 +308,11 @@ __device__ __forceinline__ double combine_fitness(int fn, const toss_params &p, 
 {
     const double rin = p.radius_inner, rout = p.radius_outer, sc = p.penalty_scaling_factor;
     double close = 0.0, far = 0.0;
-    if (f.close_min < 0.0) close = mul_(pow(__ddiv_rn(fabs(f.close_min), mul_(rin, rin)), 0.25), sc);
-    if (f.far_cnt > 0) far = mul_(pow(__ddiv_rn(__ddiv_rn(f.far_sum, (double)f.far_cnt), mul_(rout, rout)), 0.25), sc);
+    if (f.close_min < 0.0) close = mul_(tm_root4(__ddiv_rn(fabs(f.close_min), mul_(rin, rin))), sc);
+    if (f.far_cnt > 0) far = mul_(tm_root4(__ddiv_rn(__ddiv_rn(f.far_sum, (double)f.far_cnt), mul_(rout, rout))), sc);
     const double volN = -__ddiv_rn(f.vol, mul_(p.maximal_measurement_sphere_volume, (double)N));
     switch (fn) {
-    case 1: return pow(__ddiv_rn(__ddiv_rn(f.alt_sum, (double)N), p.target_squared_altitude), 0.25);
+    case 1: return tm_root4(__ddiv_rn(__ddiv_rn(f.alt_sum, (double)N), p.target_squared_altitude));
     case 2: return close;
     case 3: return far;
     case 4: return volN;
@@ -348,7 +348,7 @@ fitness_positions_kernel(int fn, toss_params p, UnitAxis axis, GridArgs g, const
         for (int w = threadIdx.x; w < g.n_words; w += blockDim.x) bits[w] = g.prev_bits[w];
         __syncthreads();
     }
-    const double c_alt = sqrt(p.target_squared_altitude);
+    const double c_alt = __dsqrt_rn(p.target_squared_altitude);
     double cmin = __longlong_as_double(0x7ff0000000000000LL), fsum = 0.0, asum = 0.0, vsum = 0.0;
     long long fcnt = 0;
     for (long long n = threadIdx.x; n < N; n += blockDim.x) {
@@ -370,7 +370,7 @@ fitness_positions_kernel(int fn, toss_params p, UnitAxis axis, GridArgs g, const
             if (j == 0) j = 1;
             if (n == N - 1) j = (N - 2 >= 1) ? N - 2 : 1;
             const double dx = sub_(px[j], px[j - 1]), dy = sub_(py[j], py[j - 1]), dz = sub_(pz[j], pz[j - 1]);
-            const double rad = __ddiv_rn(sqrt(add_(add_(mul_(dx, dx), mul_(dy, dy)), mul_(dz, dz))), 2.0);
+            const double rad = __ddiv_rn(__dsqrt_rn(add_(add_(mul_(dx, dx), mul_(dy, dy)), mul_(dz, dz))), 2.0);
             vsum += mul_((4.0 / 3.0) * kPi, mul_(mul_(rad, rad), rad));
         }
         if (need_cov)

@@ -9,33 +9,14 @@
 //     LN_pq = ln((s2+l2)/(s1+l1)) = 2 atanh(|G_pq| / (l1 + l2))
 //     hp (sum_q sigma_pq AN_pq + singA_p) = -hp_s * omega_p,
 //     omega_p = 2 atan2(r0.(r1 x r2), l0 l1 l2 + l0 (r1.r2) + l1 (r2.r0) + l2 (r0.r1))
-// Work per face-point pair: 3 sqrt, 4 div, 3 atanh (short odd series when the edge is seen under a small
-// angle, log otherwise), 1 atan2 and ~100 FMA-pipe flops -- all on the FP64 pipe; nothing to feed tensor cores.
+// Work per face-point pair on the common path (face seen under a small solid angle, edges under small
+// angles): 3 sqrt, ONE division shared by the four quotients, three 11-term atanh series, one 8-term atan
+// series, ~60 other FP64 instructions -- everything on the FP64 pipe, nothing to feed tensor cores.  Faces
+// close to the field point take the general path (separate divisions, ln-based atanh, full-range atan2).
+// Every operation is spelled out (tmath.cuh): the value is a fixed sequence of IEEE operations.
 #pragma once
 #include "common.cuh"
-
-// 2 atanh(z), 0 <= z < 1.  z^2 < 0.04: odd Taylor series through z^23 (truncation < 1e-18 relative);
-// otherwise ln((1+z)/(1-z)), whose argument is >= 1.5 so the quotient's rounding is not amplified.
-__device__ __forceinline__ double two_atanh(double z)
-{
-    const double z2 = z * z;
-    if (z2 < 0.04) {
-        double p = 1.0 / 23.0;
-        p = fma(p, z2, 1.0 / 21.0);
-        p = fma(p, z2, 1.0 / 19.0);
-        p = fma(p, z2, 1.0 / 17.0);
-        p = fma(p, z2, 1.0 / 15.0);
-        p = fma(p, z2, 1.0 / 13.0);
-        p = fma(p, z2, 1.0 / 11.0);
-        p = fma(p, z2, 1.0 / 9.0);
-        p = fma(p, z2, 1.0 / 7.0);
-        p = fma(p, z2, 1.0 / 5.0);
-        p = fma(p, z2, 1.0 / 3.0);
-        const double zz = z + z;
-        return fma(zz * z2, p, zz);
-    }
-    return log((1.0 + z) / (1.0 - z));
-}
+#include "tmath.cuh"
 
 // One face, one field point P.  fld(k) returns field k of the face record (common.cuh layout); the
 // accessor decides where it comes from (shared-memory AoS broadcast, shared-memory SoA, global SoA).
@@ -46,23 +27,44 @@ __device__ __forceinline__ void face_term(Fld fld, double Px, double Py, double 
     const double r0x = fld(0) - Px, r0y = fld(1) - Py, r0z = fld(2) - Pz;
     const double r1x = fld(3) - Px, r1y = fld(4) - Py, r1z = fld(5) - Pz;
     const double r2x = fld(6) - Px, r2y = fld(7) - Py, r2z = fld(8) - Pz;
-    const double l0 = sqrt(fma(r0z, r0z, fma(r0y, r0y, r0x * r0x)));
-    const double l1 = sqrt(fma(r1z, r1z, fma(r1y, r1y, r1x * r1x)));
-    const double l2 = sqrt(fma(r2z, r2z, fma(r2y, r2y, r2x * r2x)));
+    const double l0 = tm_sqrt(fma(r0z, r0z, fma(r0y, r0y, r0x * r0x)));
+    const double l1 = tm_sqrt(fma(r1z, r1z, fma(r1y, r1y, r1x * r1x)));
+    const double l2 = tm_sqrt(fma(r2z, r2z, fma(r2y, r2y, r2x * r2x)));
     const double Nx = fld(9), Ny = fld(10), Nz = fld(11);
-    const double hp = fma(Nz, r0z, fma(Ny, r0y, Nx * r0x));             // signed plane distance
+    const double hp = fma(Nz, r0z, fma(Ny, r0y, Nx * r0x));                  // signed plane distance
     const double hq0 = fma(fld(14), r0z, fma(fld(13), r0y, fld(12) * r0x));  // signed edge-line distances
     const double hq1 = fma(fld(17), r1z, fma(fld(16), r1y, fld(15) * r1x));
     const double hq2 = fma(fld(20), r2z, fma(fld(19), r2y, fld(18) * r2x));
-    const double ln0 = two_atanh(fld(21) / (l0 + l1));
-    const double ln1 = two_atanh(fld(22) / (l1 + l2));
-    const double ln2 = two_atanh(fld(23) / (l2 + l0));
+    const double A0 = l0 + l1, A1 = l1 + l2, A2 = l2 + l0;
     const double d12 = fma(r1z, r2z, fma(r1y, r2y, r1x * r2x));
     const double d20 = fma(r2z, r0z, fma(r2y, r0y, r2x * r0x));
     const double d01 = fma(r0z, r1z, fma(r0y, r1y, r0x * r1x));
-    const double den = fma(l2, d01, fma(l1, d20, fma(l0, d12, l0 * l1 * l2)));
-    const double omega = 2.0 * atan2(hp * fld(24), den);
-    const double S = fma(hq2, ln2, fma(hq1, ln1, hq0 * ln0)) - hp * omega;
+    const double den = fma(l2, d01, fma(l1, d20, fma(l0, d12, (l0 * l1) * l2)));
+    const double num = hp * fld(24);
+    const double G0 = fld(21), G1 = fld(22), G2 = fld(23);
+    double ln0, ln1, ln2, om;
+    bool fast = (den > 0.0) && (fabs(num) <= 0.1 * den);
+    if (fast) {
+        const double P01 = A0 * A1, P2D = A2 * den;
+        const double inv = tm_div(1.0, P01 * P2D);
+        const double i01 = P2D * inv, i2D = P01 * inv;
+        const double z0 = (G0 * A1) * i01, z1 = (G1 * A0) * i01, z2 = (G2 * den) * i2D;
+        const double q = (num * A2) * i2D;
+        fast = (z0 * z0 < 0.04) && (z1 * z1 < 0.04) && (z2 * z2 < 0.04);
+        if (fast) {
+            ln0 = tm_two_atanh_series(z0);
+            ln1 = tm_two_atanh_series(z1);
+            ln2 = tm_two_atanh_series(z2);
+            om = 2.0 * tm_atan_series<8>(q);
+        }
+    }
+    if (!fast) {
+        ln0 = tm_two_atanh(tm_div(G0, A0));
+        ln1 = tm_two_atanh(tm_div(G1, A1));
+        ln2 = tm_two_atanh(tm_div(G2, A2));
+        om = 2.0 * tm_atan2(num, den);
+    }
+    const double S = fma(-hp, om, fma(hq2, ln2, fma(hq1, ln1, hq0 * ln0)));
     ax = fma(Nx, S, ax);
     ay = fma(Ny, S, ay);
     az = fma(Nz, S, az);
@@ -110,6 +112,10 @@ __device__ __forceinline__ void mbar_fence_init()
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_drop(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive_drop.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 {

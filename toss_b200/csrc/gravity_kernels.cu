@@ -195,7 +195,78 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
+// tmath.cuh functions by id, for the bit-parity tests:
+// 0 two_atanh 1 log 2 atan2(a,b) 3 sincos 4 root8 5 root4 6 atan series (8 terms) 7 a/b 8 sqrt
+__global__ void math_probe_kernel(int fn, const double *__restrict__ a, const double *__restrict__ b, int64_t n,
+                                  double *__restrict__ out, double *__restrict__ out2)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r = 0.0, r2 = 0.0;
+    switch (fn) {
+    case 0: r = tm_two_atanh(a[i]); break;
+    case 1: r = tm_log(a[i]); break;
+    case 2: r = tm_atan2(a[i], b[i]); break;
+    case 3: tm_sincos(a[i], r, r2); break;
+    case 4: r = tm_root8(a[i]); break;
+    case 5: r = tm_root4(a[i]); break;
+    case 6: r = tm_atan_series<8>(a[i]); break;
+    case 7: r = tm_div(a[i], b[i]); break;
+    case 8: r = tm_sqrt(a[i]); break;
+    default: r = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    out[i] = r;
+    if (out2) out2[i] = r2;
+}
+
+// tm_div / tm_sqrt against the guarded IEEE intrinsics on pseudo-random operands spanning 2^-200 .. 2^200
+__global__ void div_sqrt_selftest_kernel(unsigned long long seed, int iters, unsigned long long *mismatch)
+{
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ULL * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x + 1);
+    unsigned long long bad_div = 0, bad_sqrt = 0;
+    for (int i = 0; i < iters; ++i) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        unsigned long long m1 = x & 0x000fffffffffffffULL;
+        int e1 = (int)((x >> 52) % 401) - 200;
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        unsigned long long m2 = x & 0x000fffffffffffffULL;
+        int e2 = (int)((x >> 52) % 401) - 200;
+        const double a = __longlong_as_double((long long)(m1 | ((unsigned long long)(e1 + 1023) << 52)));
+        const double b = __longlong_as_double((long long)(m2 | ((unsigned long long)(e2 + 1023) << 52)));
+        if (__double_as_longlong(tm_div(a, b)) != __double_as_longlong(__ddiv_rn(a, b))) ++bad_div;
+        if (__double_as_longlong(tm_sqrt(a)) != __double_as_longlong(__dsqrt_rn(a))) ++bad_sqrt;
+    }
+    if (bad_div) atomicAdd(&mismatch[0], bad_div);
+    if (bad_sqrt) atomicAdd(&mismatch[1], bad_sqrt);
+}
+
 // ---------------------------------------- launchers ---------------------------------------------
+int launch_math_probe(toss_ctx *ctx, int fn, const double *a, const double *b, int64_t n, double *out, double *out2,
+                      cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fn, a, b, n, out, out2);
+    ctx->launches++;
+    TOSS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_div_sqrt_selftest(toss_ctx *ctx, int64_t samples, int64_t *bad_div, int64_t *bad_sqrt)
+{
+    unsigned long long *d = nullptr, h[2] = {0, 0};
+    TOSS_CHECK_CUDA(cudaMalloc(&d, 16));
+    TOSS_CHECK_CUDA(cudaMemset(d, 0, 16));
+    const int blocks = ctx->sm_count * 8, threads = 256;
+    const int iters = (int)((samples + (int64_t)blocks * threads - 1) / ((int64_t)blocks * threads));
+    div_sqrt_selftest_kernel<<<blocks, threads>>>(0x1234567ULL, iters, d);
+    ctx->launches++;
+    TOSS_CHECK_CUDA(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *bad_div = (int64_t)h[0];
+    *bad_sqrt = (int64_t)h[1];
+    return 0;
+}
+
 int launch_gravity(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc, double *d_pot, cudaStream_t st)
 {
     TOSS_REQUIRE(ctx && ctx->d_face_aos, "toss_gravity_eval: no mesh uploaded");

@@ -14,8 +14,10 @@
 //   RESIDENT  the flat SoA face table fits in shared memory (lllp, llp): TMA-copied once per CTA;
 //             warps then run completely independently.
 //   STREAM    (lp, full) the table streams through a 3-stage ring of 25.6 KB SoA tiles filled by TMA
-//             bulk copies; the 8 warps of a CTA sweep the tiles in lock step (one RHS evaluation per
-//             warp per sweep) so every byte fetched from L2 is used by 8 trajectories.
+//             bulk copies (mbarrier full/empty pairs); the 8 warps of a CTA consume the same tile
+//             sequence, one RHS evaluation per warp per sweep, coupled only through the ring (a warp can
+//             run at most two tiles ahead), so every byte fetched from L2 is used by 8 trajectories.
+//             There is no CTA-wide barrier after start-up: warps retire from the ring with arrive_drop.
 #include "gravity.cuh"
 
 #define TOSS_RK_QUAL __constant__
@@ -56,7 +58,9 @@ __global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a
     double *wstate = reinterpret_cast<double *>(bars + 8) + (size_t)wid * warp_state_doubles(a.n_man);
     double *sy = wstate, *sk = wstate + 6, *meta = wstate + 84, *seg_t = wstate + 86, *sdv = seg_t + (a.n_man + 2);
 
+    int *live = reinterpret_cast<int *>(bars + 7);   // warps that have not retired yet (STREAM)
     if (tid == 0) {
+        *live = kK2Warps;
         if (kStream) {
             for (int s = 0; s < kK2Stages; ++s) {
                 mbar_init(&bars[s], 1);
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a
     uint32_t tile_it = 0;     // tiles consumed so far by this warp (== by every warp: lock step)
 
     // warp-uniform trajectory state
-    bool active = false, queue_empty = false;
+    bool active = false, queue_empty = false, counted_out = false;
     int traj = -1, stage = 0, seg = 0, nseg = 0, nk = 0, steps = 0, clipped = 0, after_accept = 0, status = 0;
     int n_acc = 0, n_rej = 0, n_ev = 0;
     long long n_rhs = 0;
@@ -179,10 +183,33 @@ __global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a
                 if (lane == 0) a.seg_start[(size_t)traj * (a.n_man + 2)] = 0;
             }
         }
-        if (kStream) {
-            if (!__syncthreads_or(active ? 1 : 0)) break;
-        } else {
-            if (!active) break;
+        if (!active) {
+            // queue drained, nothing in hand: this warp retires.  RESIDENT: just leave.  STREAM: leave the
+            // tile ring cleanly -- wait until every tile this warp released has been released by all, then
+            // arrive_drop on each `empty` barrier (counts as this warp's arrival for the tile it will not
+            // read and removes it from all later phases).  Warp 0 owns the producer thread: it stays as an
+            // idle consumer/producer until the other warps are gone.
+            if (!kStream) break;
+            if (wid != 0) {
+                for (int s = 0; s < kK2Stages; ++s) {
+                    // last tile of stage s this warp has consumed: largest it < tile_it with it % kK2Stages == s
+                    if (tile_it > (uint32_t)s) {
+                        const uint32_t last = tile_it - 1 - ((tile_it - 1 - s) % kK2Stages);
+                        mbar_wait(&bars[kK2Stages + s], (last / kK2Stages) & 1u);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_drop(&bars[kK2Stages + s]);
+                }
+                __syncwarp();
+                if (lane == 0) atomicSub(live, 1);
+                break;
+            }
+            if (!counted_out) {
+                counted_out = true;
+                if (lane == 0) atomicSub(live, 1);
+                __syncwarp();
+            }
+            if (*reinterpret_cast<volatile int *>(live) == 0) break;
         }
 
         // ------------------------------------------------ stage point: ys = y + dt sum_j a_ij k_j
@@ -323,7 +350,7 @@ __global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a
                 status = 2;
             } else {
                 double corr = 1.0;
-                if (err != 0.0) corr = mul_(0.8, pow(__ddiv_rn(tol, err), 0.125));
+                if (err != 0.0) corr = mul_(0.8, tm_root8(__ddiv_rn(tol, err)));
                 const double newdt = (corr != 0.0) ? mul_(corr, dt) : dt;
                 if (err > tol) {
                     ++n_rej;
