@@ -71,7 +71,7 @@ typedef struct {
     size_t n_seg;       /* int32  [pop]                                                        */
     size_t counters;    /* toss_counters [pop]                                                 */
     size_t collision;   /* int32  [pop]                collision_detected                      */
-    size_t queue;       /* int32  [4]                  work-queue cursor (internal)            */
+    size_t queue;       /* int32  [4 + 2 pop]          work-queue cursor | order | predicted cost (internal) */
     size_t total_bytes;
 } toss_ws_layout;
 

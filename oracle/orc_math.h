@@ -17,15 +17,15 @@
 
 #define ORC_FMA(a, b, c) __builtin_fma((a), (b), (c))
 
-/* 2 atanh(z) for z*z < 0.04: 2z (1 + z^2 (1/3 + z^2/5 + ... + z^20/23)) */
-static inline double orc_two_atanh_series(double z)
+/* 2 atanh(z) = 2z (1 + z^2 (1/3 + z^2/5 + ...)), nterms coefficients: 11 for z*z < 0.04, 5 for z*z < 0.0025 */
+static inline double orc_two_atanh_series_n(double z, double z2, int nterms)
 {
-    const double z2 = z * z;
-    double p = ORC_ATANH[10];
-    for (int k = 9; k >= 0; --k) p = ORC_FMA(p, z2, ORC_ATANH[k]);
+    double p = ORC_ATANH[nterms - 1];
+    for (int k = nterms - 2; k >= 0; --k) p = ORC_FMA(p, z2, ORC_ATANH[k]);
     const double zz = z + z;
     return ORC_FMA(zz * z2, p, zz);
 }
+static inline double orc_two_atanh_series(double z) { return orc_two_atanh_series_n(z, z * z, 11); }
 
 /* ln(x), x > 0 normal: x = 2^e m, m in [sqrt(1/2), sqrt(2)); ln m = 2 atanh((m-1)/(m+1)) */
 static inline double orc_log(double x)
@@ -53,14 +53,15 @@ static inline double orc_two_atanh(double z)
     return orc_log((1.0 + z) / (1.0 - z));
 }
 
-/* atan(t) = t (1 + t^2 (-1/3 + t^2/5 - ...)), `nterms` coefficients */
-static inline double orc_atan_series(double t, int nterms)
+/* atan(t) = t (1 + t^2 (-1/3 + t^2/5 - ...)), nterms coefficients: 22 for |t| <= tan(pi/8), 8 for |t| <= 0.1,
+ * 3 for t*t < 1e-4 */
+static inline double orc_atan_series_n(double t, double t2, int nterms)
 {
-    const double t2 = t * t;
     double p = ORC_ATAN[nterms - 1];
     for (int k = nterms - 2; k >= 0; --k) p = ORC_FMA(p, t2, ORC_ATAN[k]);
     return ORC_FMA(t * t2, p, t);
 }
+static inline double orc_atan_series(double t, int nterms) { return orc_atan_series_n(t, t * t, nterms); }
 
 /* atan2(y, x): a = min/max in [0,1]; a > tan(pi/8) -> (a-1)/(a+1) + pi/4; 22-term series on |t| <= tan(pi/8) */
 static inline double orc_atan2(double y, double x)

@@ -213,12 +213,13 @@ static inline void face_term(const double *rc, const double P[3], double *ax, do
         const double i01 = P2D * inv, i2D = P01 * inv;
         const double z0 = (G[0] * A1) * i01, z1 = (G[1] * A0) * i01, z2 = (G[2] * den) * i2D;
         const double q = (num * A2) * i2D;
-        fast = (z0 * z0 < 0.04) && (z1 * z1 < 0.04) && (z2 * z2 < 0.04);
+        const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, qs = q * q;
+        fast = (z0s < 0.04) && (z1s < 0.04) && (z2s < 0.04);
         if (fast) {
-            ln0 = orc_two_atanh_series(z0);
-            ln1 = orc_two_atanh_series(z1);
-            ln2 = orc_two_atanh_series(z2);
-            om = 2.0 * orc_atan_series(q, 8);
+            ln0 = orc_two_atanh_series_n(z0, z0s, 11);
+            ln1 = orc_two_atanh_series_n(z1, z1s, 11);
+            ln2 = orc_two_atanh_series_n(z2, z2s, 11);
+            om = 2.0 * orc_atan_series_n(q, qs, 8);
         }
     }
     if (!fast) {
@@ -398,6 +399,7 @@ static int integrate_segment(const orc_mesh *m, const orc_params *p, double t0, 
                 cnt->n_rhs++;
             }
             double err = 0.0, tol = 0.0;
+            int finite = 1;
             for (int c = 0; c < 6; ++c) {
                 double s8 = 0.0, se = 0.0;
                 for (int j = 0; j < 13; ++j) {
@@ -409,11 +411,12 @@ static int integrate_segment(const orc_mesh *m, const orc_params *p, double t0, 
                 double tl = p->atol + p->rtol * fabs(y[c]) + p->rtol * fabs(s8);
                 if (e > err) err = e;
                 if (tl > tol) tol = tl;
+                if (!isfinite(e) || !isfinite(tl)) finite = 0; /* a NaN would lose every comparison above */
             }
             double corr = 1.0;
             if (err != 0.0) corr = 0.8 * orc_root8(tol / err);
             newdt = (corr != 0.0) ? corr * dt : dt;
-            if (!(err == err) || !(tol == tol)) { /* NaN */
+            if (!finite) { /* NaN / Inf state */
                 cnt->status = 2;
                 return 0;
             }

@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 
 _CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = _CSRC / "libtoss_b200.so"
+LIB_PATH = Path(os.environ.get("TOSS_B200_LIB", _CSRC / "libtoss_b200.so"))   # override: developer experiments only
 
 c_double_p = C.POINTER(C.c_double)
 

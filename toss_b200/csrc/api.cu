@@ -110,6 +110,19 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
     ctx->V = V;
     ctx->F = F;
     ctx->Grho = kGravConst * density;
+    {   // volume and centre of mass by the divergence theorem (signed tetrahedra from the origin)
+        double vol = 0.0, c[3] = {0.0, 0.0, 0.0};
+        for (int f = 0; f < F; ++f) {
+            const double *a = h_verts + 3 * (size_t)h_faces[3 * f], *b = h_verts + 3 * (size_t)h_faces[3 * f + 1],
+                         *d = h_verts + 3 * (size_t)h_faces[3 * f + 2];
+            const double v6 = a[0] * (b[1] * d[2] - b[2] * d[1]) + a[1] * (b[2] * d[0] - b[0] * d[2]) +
+                              a[2] * (b[0] * d[1] - b[1] * d[0]);
+            vol += v6 / 6.0;
+            for (int k = 0; k < 3; ++k) c[k] += (a[k] + b[k] + d[k]) / 4.0 * v6 / 6.0;
+        }
+        ctx->GM = ctx->Grho * vol;
+        for (int k = 0; k < 3; ++k) ctx->com[k] = vol != 0.0 ? c[k] / vol : 0.0;
+    }
     ctx->Fpad32 = (F + 31) / 32 * 32;
     ctx->n_aos_tiles = (F + kAosTileFaces - 1) / kAosTileFaces;
     ctx->n_soa_tiles = (F + kSoaTileFaces - 1) / kSoaTileFaces;

@@ -19,7 +19,10 @@
 constexpr int kFaceFields = 25;
 constexpr int kAosStride = 26;          // AoS record padded to 208 B = 13 x 16 B (LDS.128 broadcast reads)
 constexpr int kAosTileFaces = 64;       // K1 (thread-per-point) TMA tile: 64 x 208 B = 13 312 B
-constexpr int kSoaTileFaces = 128;      // K2 (lane-per-face) TMA tile: 25 x 128 x 8 B = 25 600 B
+#ifndef SOA_TILE_FACES
+#define SOA_TILE_FACES 128
+#endif
+constexpr int kSoaTileFaces = SOA_TILE_FACES;   // K2 (lane-per-face) TMA tile: 25 x 128 x 8 B = 25 600 B
 constexpr int kSoaTileDoubles = kFaceFields * kSoaTileFaces;
 constexpr double kPadVertex = 1.0e9;    // padding faces sit here with N = n = |G| = 2A = 0 -> contribute exactly 0
 constexpr double kGravConst = 6.67430e-11;   // CODATA-2018, as polyhedral_gravity >= 2
@@ -34,6 +37,7 @@ struct toss_ctx {
     int n_aos_tiles = 0;   // ceil(F / 64)
     int n_soa_tiles = 0;   // ceil(F / 128)
     double Grho = 0.0;
+    double GM = 0.0, com[3] = {0.0, 0.0, 0.0};   // G rho V and the centre of mass (work-queue cost predictor)
     double *d_face_aos = nullptr;    // [n_aos_tiles*64][26]
     double *d_face_soa = nullptr;    // [25][Fpad32]
     double *d_face_tiles = nullptr;  // [n_soa_tiles][25][128]

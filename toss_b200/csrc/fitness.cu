@@ -338,7 +338,7 @@ fitness_positions_kernel(int fn, toss_params p, UnitAxis axis, GridArgs g, const
 {
     extern __shared__ __align__(16) unsigned char fsm[];
     uint32_t *bits = reinterpret_cast<uint32_t *>(fsm);
-    int *shell = reinterpret_cast<int *>(bits + g.n_words);
+    int *shell = reinterpret_cast<int *>(bits + ((g.n_words + 1) & ~1));   // keeps the 8-byte data behind it aligned
     __shared__ double sc_d[kFitThreads / 32];
     __shared__ long long sc_l[kFitThreads / 32];
     const int b = blockIdx.x;
@@ -406,7 +406,7 @@ fitness_knots_kernel(toss_params p, UnitAxis axis, GridArgs g, const double *__r
 {
     extern __shared__ __align__(16) unsigned char fsm[];
     uint32_t *bits = reinterpret_cast<uint32_t *>(fsm);
-    int *shell = reinterpret_cast<int *>(bits + g.n_words);
+    int *shell = reinterpret_cast<int *>(bits + ((g.n_words + 1) & ~1));   // keeps the 8-byte data behind it aligned
     long long *seg_e = reinterpret_cast<long long *>(shell + ((g.nr + 1) & ~1));
     __shared__ double sc_d[kFitThreads / 32];
     __shared__ long long sc_l[kFitThreads / 32];
@@ -579,7 +579,7 @@ int launch_dense_eval(toss_ctx *ctx, const double *kt, const double *ky, const d
 
 static int fitness_smem_bytes(const toss_ctx *ctx, const GridArgs &g, int n_man, size_t *out)
 {
-    const size_t b = (size_t)g.n_words * 4 + (size_t)((g.nr + 1) & ~1) * 4 + sizeof(long long) * (n_man + 2) + 16;
+    const size_t b = (size_t)((g.n_words + 1) & ~1) * 4 + (size_t)((g.nr + 1) & ~1) * 4 + sizeof(long long) * (n_man + 2) + 16;
     TOSS_REQUIRE(b <= (size_t)ctx->max_smem_optin - 1024,
                  "voxel grid too fine for the shared-memory bitmap (nr*ntheta*nphi bits must fit in ~220 KB)");
     *out = b;

@@ -42,6 +42,8 @@ __device__ __forceinline__ void face_term(Fld fld, double Px, double Py, double 
     const double den = fma(l2, d01, fma(l1, d20, fma(l0, d12, (l0 * l1) * l2)));
     const double num = hp * fld(24);
     const double G0 = fld(21), G1 = fld(22), G2 = fld(23);
+    // (measured alternatives, both slower: a shorter far-field series tier -- near- and far-side faces share a
+    //  warp, so both tiers execute -- and computing the common path unconditionally -- register pressure)
     double ln0, ln1, ln2, om;
     bool fast = (den > 0.0) && (fabs(num) <= 0.1 * den);
     if (fast) {
@@ -50,15 +52,16 @@ __device__ __forceinline__ void face_term(Fld fld, double Px, double Py, double 
         const double i01 = P2D * inv, i2D = P01 * inv;
         const double z0 = (G0 * A1) * i01, z1 = (G1 * A0) * i01, z2 = (G2 * den) * i2D;
         const double q = (num * A2) * i2D;
-        fast = (z0 * z0 < 0.04) && (z1 * z1 < 0.04) && (z2 * z2 < 0.04);
+        const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2;
+        fast = (z0s < 0.04) && (z1s < 0.04) && (z2s < 0.04);
         if (fast) {
-            ln0 = tm_two_atanh_series(z0);
-            ln1 = tm_two_atanh_series(z1);
-            ln2 = tm_two_atanh_series(z2);
-            om = 2.0 * tm_atan_series<8>(q);
+            ln0 = tm_two_atanh_series_n<11>(z0, z0s);
+            ln1 = tm_two_atanh_series_n<11>(z1, z1s);
+            ln2 = tm_two_atanh_series_n<11>(z2, z2s);
+            om = 2.0 * tm_atan_series_n<8>(q, q * q);
         }
     }
-    if (!fast) {
+    if (!fast) {   // face close to the field point: separate divisions, ln-based atanh, full-range atan2
         ln0 = tm_two_atanh(tm_div(G0, A0));
         ln1 = tm_two_atanh(tm_div(G1, A1));
         ln2 = tm_two_atanh(tm_div(G2, A2));

@@ -18,14 +18,30 @@
 //             sequence, one RHS evaluation per warp per sweep, coupled only through the ring (a warp can
 //             run at most two tiles ahead), so every byte fetched from L2 is used by 8 trajectories.
 //             There is no CTA-wide barrier after start-up: warps retire from the ring with arrive_drop.
+#include <stdlib.h>
+
 #include "gravity.cuh"
 
 #define TOSS_RK_QUAL __constant__
 #include "rk8713m_tableau.h"
 
-constexpr int kK2Warps = 8;
+#ifndef K2_WARPS
+#define K2_WARPS 8
+#endif
+#ifndef K2_STAGES
+#define K2_STAGES 3
+#endif
+#ifndef K2_MINBLOCKS
+#define K2_MINBLOCKS 2
+#endif
+#ifndef K2_UNROLL
+#define K2_UNROLL 2
+#endif
+constexpr int kK2Warps = K2_WARPS;
 constexpr int kK2Threads = kK2Warps * 32;
-constexpr int kK2Stages = 3;
+constexpr int kK2Stages = K2_STAGES;
+constexpr int kK2Unroll = K2_UNROLL;
+constexpr int kK2BarSlots = 2 * K2_STAGES + 2;   // full[] | empty[] | live counter | pad
 constexpr int kSoaTileBytes = kSoaTileDoubles * 8;
 
 struct StepArgs {
@@ -41,6 +57,7 @@ struct StepArgs {
     // workspace
     double *knots_t, *knots_y, *knots_f, *intervals;
     int32_t *seg_start, *n_seg, *collision, *queue;
+    const int32_t *order;      // queue position -> trajectory index (longest predicted first), or NULL
     toss_counters *counters;
 };
 
@@ -48,17 +65,17 @@ struct StepArgs {
 __host__ __device__ inline int warp_state_doubles(int n_man) { return 6 + 78 + 2 + (n_man + 2) + 3 * (n_man > 0 ? n_man : 1); }
 
 template <bool kStream>
-__global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a)
+__global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int mesh_doubles = kStream ? kK2Stages * kSoaTileDoubles : kFaceFields * a.Fpad32;
     double *mesh = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(mesh + mesh_doubles);   // full[3] empty[3] (STREAM) / full[1]
-    double *wstate = reinterpret_cast<double *>(bars + 8) + (size_t)wid * warp_state_doubles(a.n_man);
+    double *wstate = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)wid * warp_state_doubles(a.n_man);
     double *sy = wstate, *sk = wstate + 6, *meta = wstate + 84, *seg_t = wstate + 86, *sdv = seg_t + (a.n_man + 2);
 
-    int *live = reinterpret_cast<int *>(bars + 7);   // warps that have not retired yet (STREAM)
+    int *live = reinterpret_cast<int *>(bars + 2 * kK2Stages);   // warps that have not retired yet (STREAM)
     if (tid == 0) {
         *live = kK2Warps;
         if (kStream) {
@@ -115,7 +132,7 @@ __global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a
             if (nxt >= a.pop) {
                 queue_empty = true;
             } else {
-                traj = nxt;
+                traj = a.order ? a.order[nxt] : nxt;
                 active = true;
                 // x = hstack(initial_condition, chromosome)  (udp_initial_condition.py:117-120)
                 auto X = [&](int i) -> double {
@@ -250,7 +267,7 @@ __global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a
                 mbar_wait(&bars[s], (tile_it / kK2Stages) & 1u);
                 if (active) {
                     const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
-#pragma unroll 2
+#pragma unroll kK2Unroll
                     for (int f = 0; f < kSoaTileFaces; f += 32) {
                         const double *col = tile + f;
                         face_term<false>([col](int k) { return col[k * kSoaTileFaces]; }, Px, Py, Pz, ax, ay, az, pv);
@@ -261,7 +278,7 @@ __global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a
             }
         } else {
             const int Fp = a.Fpad32;
-#pragma unroll 2
+#pragma unroll kK2Unroll
             for (int f = lane; f < Fp; f += 32) {
                 const double *col = mesh + f;
                 face_term<false>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, ax, ay, az, pv);
@@ -396,6 +413,131 @@ __global__ void __launch_bounds__(kK2Threads, 2) stepper_kernel(const StepArgs a
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Work-queue ordering.  Trajectory lengths spread 4x (1.3 k .. 5 k RHS evaluations) and there are only ~1.7
+// trajectories per resident warp, so the order in which warps pull them decides the tail.  One thread per
+// trajectory pre-integrates the same chromosome around a softened POINT MASS (G rho V at the centre of mass) with
+// the same RK8(7)-13M controller at rtol = atol = 1e-9; its RHS count is the sort key (descending).  The order
+// only schedules: results are written by trajectory index and do not depend on it.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPredMaxMan = 16;
+constexpr double kPredTol = 1e-9, kPredSoft2 = 1.0e6;   // 1 km softening: the proxy must survive a pass through the body
+
+__device__ __forceinline__ void pm_rhs(const double *y, double GM, double cx, double cy, double cz, double *f)
+{
+    const double x = y[0] - cx, yy = y[1] - cy, z = y[2] - cz;
+    const double r2 = x * x + yy * yy + z * z + kPredSoft2;
+    const double g = -GM / (r2 * sqrt(r2));
+    f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
+    f[3] = g * x; f[4] = g * yy; f[5] = g * z;
+}
+
+__global__ void __launch_bounds__(128) cost_predict_kernel(const StepArgs a, double GM, double cx, double cy,
+                                                           double cz, int32_t *__restrict__ cost)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.pop) return;
+    auto X = [&](int k) -> double { return k < a.n_fixed ? a.fixed[k] : a.x[(size_t)i * a.dim + (k - a.n_fixed)]; };
+    double y[6] = {X(0), X(1), X(2), X(3) * X(4), X(3) * X(5), X(3) * X(6)};
+    double tm[kPredMaxMan + 2];
+    int idx[kPredMaxMan];
+    const int M = a.n_man;
+    for (int k = 0; k < M; ++k) {
+        tm[k + 1] = (double)(int32_t)X(7 + 5 * k);
+        idx[k] = k;
+    }
+    for (int p = 1; p < M; ++p) {   // insertion sort by time
+        const int v = idx[p];
+        int j = p;
+        while (j > 0 && tm[idx[j - 1] + 1] > tm[v + 1]) {
+            idx[j] = idx[j - 1];
+            --j;
+        }
+        idx[j] = v;
+    }
+    const double t_end = (double)(int32_t)a.p.final_time;
+    double t = (double)(int32_t)a.p.start_time;
+    int n_rhs = 0;
+    double k[13][6];
+    for (int s = 0; s <= M && n_rhs < 60000; ++s) {
+        const double tf = s < M ? tm[idx[s] + 1] : t_end;
+        if (s > 0) {
+            const int m = idx[s - 1];
+            const double mag = X(8 + 5 * m);
+            y[3] = mag * X(9 + 5 * m); y[4] = mag * X(10 + 5 * m); y[5] = mag * X(11 + 5 * m);
+        }
+        double dt = a.p.initial_time_step;
+        pm_rhs(y, GM, cx, cy, cz, k[0]);
+        ++n_rhs;
+        while (t < tf && n_rhs < 60000) {
+            bool clipped = false;
+            if (t + dt > tf) {
+                dt = tf - t;
+                clipped = true;
+            }
+            for (int st = 1; st < 13; ++st) {
+                double ys[6];
+                for (int c = 0; c < 6; ++c) {
+                    double acc = 0.0;
+                    for (int j = 0; j < st; ++j) acc = fma(TOSS_RK_A[13 * st + j], k[j][c], acc);
+                    ys[c] = fma(dt, acc, y[c]);
+                }
+                pm_rhs(ys, GM, cx, cy, cz, k[st]);
+            }
+            n_rhs += 12;
+            double err = 0.0, tol = 0.0, dy[6];
+            for (int c = 0; c < 6; ++c) {
+                double s8 = 0.0, se = 0.0;
+                for (int j = 0; j < 13; ++j) {
+                    s8 = fma(TOSS_RK_B8[j], k[j][c], s8);
+                    se = fma(TOSS_RK_E[j], k[j][c], se);
+                }
+                dy[c] = dt * s8;
+                err = fmax(err, fabs(dt * se));
+                tol = fmax(tol, kPredTol + kPredTol * fabs(y[c]) + kPredTol * fabs(s8));
+            }
+            if (!(err == err)) break;
+            const double corr = err != 0.0 ? 0.8 * sqrt(sqrt(sqrt(tol / err))) : 1.0;
+            const double newdt = corr * dt;
+            if (err > tol) {
+                dt = newdt;
+                if (!(dt > 0.0)) break;
+                continue;
+            }
+            t = clipped ? tf : t + dt;
+            for (int c = 0; c < 6; ++c) y[c] += dy[c];
+            dt = newdt;
+            pm_rhs(y, GM, cx, cy, cz, k[0]);
+            ++n_rhs;
+        }
+        t = tf;
+    }
+    cost[i] = n_rhs;
+}
+
+// one block: counting sort of the predicted costs, longest first (order within a bin is irrelevant)
+__global__ void __launch_bounds__(1024) cost_sort_kernel(const int32_t *__restrict__ cost, int pop,
+                                                         int32_t *__restrict__ order)
+{
+    __shared__ int hist[4096];
+    for (int b = threadIdx.x; b < 4096; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    auto key = [](int c) { c >>= 2; return c < 0 ? 0 : (c > 4095 ? 4095 : c); };
+    for (int i = threadIdx.x; i < pop; i += blockDim.x) atomicAdd(&hist[key(cost[i])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int b = 4095; b >= 0; --b) {
+            const int h = hist[b];
+            hist[b] = run;
+            run += h;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < pop; i += blockDim.x) order[atomicAdd(&hist[key(cost[i])], 1)] = i;
+}
+
 int toss_workspace_layout_impl(int pop, int n_man, int knot_cap, toss_ws_layout *out)
 {
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -408,7 +550,7 @@ int toss_workspace_layout_impl(int pop, int n_man, int knot_cap, toss_ws_layout 
     out->n_seg = o;     o = up(o + sizeof(int32_t) * (size_t)pop);
     out->counters = o;  o = up(o + sizeof(toss_counters) * (size_t)pop);
     out->collision = o; o = up(o + sizeof(int32_t) * (size_t)pop);
-    out->queue = o;     o = up(o + sizeof(int32_t) * 4);
+    out->queue = o;     o = up(o + sizeof(int32_t) * (4 + 2 * (size_t)pop));   // cursor | order[pop] | cost[pop]
     out->total_bytes = o;
     return 0;
 }
@@ -450,13 +592,24 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     a.queue = reinterpret_cast<int32_t *>(ws + L.queue);
     a.counters = reinterpret_cast<toss_counters *>(ws + L.counters);
     TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 16, st));
+    // longest-processing-time-first: with ~1.7 trajectories per warp slot and a 4x spread of trajectory lengths the
+    // tail of an index-ordered queue costs ~40 %; a cheap point-mass pre-integration predicts the step counts.
+    a.order = nullptr;
+    static const bool lpt = getenv("TOSS_B200_LPT") != nullptr;   // experimental: the point-mass proxy predicts poorly (r = 0.25)
+    if (lpt && n_man <= kPredMaxMan && pop > kK2Warps) {
+        int32_t *order = a.queue + 4, *cost = order + pop;
+        cost_predict_kernel<<<(pop + 127) / 128, 128, 0, st>>>(a, ctx->GM, ctx->com[0], ctx->com[1], ctx->com[2], cost);
+        cost_sort_kernel<<<1, 1024, 0, st>>>(cost, pop, order);
+        ctx->launches += 2;
+        a.order = order;
+    }
 
-    const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + 64;
+    const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8;
     const size_t resident_bytes = (size_t)kFaceFields * ctx->Fpad32 * 8 + state_bytes;
     const size_t stream_bytes = (size_t)kK2Stages * kSoaTileBytes + state_bytes;
-    const bool resident = resident_bytes <= 100 * 1024;   // two CTAs per SM keep their own copy
+    const bool resident = resident_bytes <= (size_t)(200 / K2_MINBLOCKS) * 1024;   // every CTA on an SM keeps its own copy
     int ctas = (pop + kK2Warps - 1) / kK2Warps;
-    const int max_ctas = 2 * ctx->sm_count;
+    const int max_ctas = K2_MINBLOCKS * ctx->sm_count;
     if (ctas > max_ctas) ctas = max_ctas;
     if (resident) {
         TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
