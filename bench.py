@@ -8,8 +8,10 @@ A "step" is ONE evaluation of the whole hot path over one population:
 Workload (BASELINE.json configs[4], the scaling benchmark; configs[1] -- the 1 M-point gravity microbench on
 the same lp mesh -- is reported beside it in `gravity_microbench`): lp 67P mesh (1828 faces), 1 spacecraft,
 2 manoeuvres, 7-day window, default_cfg.toml tolerances, 6048 samples, 6x8x17 voxel grid; synthetic
-"init-like" chromosomes, 4096 per GPU (32768 on 8 GPUs), sharded as contiguous islands with no
-data-path collective except one all-gather of the fitness vector.
+"init-like" chromosomes.  N = 1 is configs[4] itself: a population of 32768 on one B200.  For N > 1
+the default is WEAK scaling -- one such 32768-chromosome island per GPU (`--scaling strong` instead splits ONE
+32768 population over the N GPUs, 4096 each at N = 8).  Islands are contiguous row slices; the only collective is
+one all-gather of the fitness vector.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pop-per-gpu P] [--mesh lp]
 """
@@ -132,7 +134,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "candidate_trajectories_per_sec", "value": value, "unit": "trajectories/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, pop_total),
         "gravity_evals_per_sec": n_rhs / dt,
         "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": cores, "kind": "port",
@@ -287,7 +289,7 @@ def run_ours(args):
         line = {
             "metric": "candidate_trajectories_per_sec", "value": value, "unit": "trajectories/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, pop_total),
             "gravity_evals_per_sec": n_rhs_total * args.steps / (ms * 1e-3),
             "gravity_evals_per_trajectory": n_rhs_total / pop_total,
@@ -344,7 +346,7 @@ def cpu_baseline(O, args, xs_all):
     cores = os.cpu_count() or 1
     v, f = O.load_mesh(args.mesh)
     mesh = O.Mesh(v, f)
-    sample = min(len(xs_all), 40 * cores)      # ~15-25 s of host work on the lp mesh
+    sample = min(len(xs_all), 160 * cores)     # ~15-25 s of host work on the lp mesh
     t0 = time.perf_counter()
     r = O.population_fitness(mesh, O.default_params(), O.default_grid(), xs_all[:sample], FIXED_POS, N_MAN, threads=cores)
     dt = time.perf_counter() - t0
@@ -359,13 +361,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pop-per-gpu", type=int, default=4096)
+    ap.add_argument("--pop-per-gpu", type=int, default=32768)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--mesh", default="lp", choices=["lllp", "llp", "lp", "full"])
-    ap.add_argument("--knot-cap", type=int, default=2048)
+    ap.add_argument("--knot-cap", type=int, default=1024)
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true")
     args = ap.parse_args()
+    if args.scaling == "strong":
+        if args.pop_per_gpu % args.gpus:
+            raise SystemExit("--scaling strong: the population must divide by --gpus")
+        args.pop_per_gpu //= args.gpus
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -43,7 +43,7 @@ class udp_initial_condition:
         self.lower_bounds = lower_bounds
         self.upper_bounds = upper_bounds
         self.args.problem.number_of_spacecraft = 1   # (sic) the reference sets this unused singular key (:103)
-        self.knot_capacity = 4096
+        self.knot_capacity = 2048                    # knots per trajectory in the device workspace (status 3 if exceeded)
         self.last_batch = None                       # counters / collision flags of the latest batch
 
     # ------------------------------------------------------------------------------------------
