@@ -237,3 +237,30 @@ def test_is_outside_and_evaluable_api():
     assert np.array_equal(rhs[:3], [1.0, 2.0, 3.0]) and np.allclose(rhs[3:], -acc, rtol=1e-14)
     with pytest.raises(NotImplementedError):
         T.compute_trajectory(G.X0, _args(), lambda t, y, args: y)
+
+
+def test_use_case_driver_sequential_spacecraft(tmp_path):
+    """toss.py:71-191 at BASELINE configs[0] size (lllp mesh, 1 manoeuvre, pop 16, 2 generations), 2 spacecraft:
+    one batch_fitness call per generation, champions improve monotonically, the first champion's voxels reach the
+    second spacecraft through bool_tensor, four CSV files are written."""
+    import toss_b200 as T
+    from toss_b200 import driver
+    args = T.setup_parameters()
+    args.mesh.mesh_path = "3dmeshes/churyumov-gerasimenko_lllp.pk"
+    (args.mesh.body, args.mesh.vertices, args.mesh.faces,
+     args.mesh.largest_body_protuberant) = T.create_mesh(args.mesh.mesh_path)
+    args.problem.number_of_maneuvers = 1
+    args.problem.number_of_spacecrafts = 2
+    args.problem.final_time = 86400
+    args.optimization.population_size = 16
+    args.optimization.number_of_generations = 2
+    pr = args.problem
+    init = np.array_split([pr.initial_x, pr.initial_y, pr.initial_z] * 2, 2)
+    lb, ub = T.setup_initial_state_domain(init[0], pr.start_time, pr.final_time, 1, 2, args.chromosome)
+    rt, cf, cx, fl = driver.run_optimization(args, init, lb, ub, seed=1)
+    assert fl.shape == (2, 2) and np.all(np.diff(fl, axis=1) <= 0)
+    assert len(cx) == 2 and len(cx[0]) == len(lb) and cf[0][0] == fl[0, -1]
+    assert args.problem.bool_tensor.any()
+    # the champion of spacecraft 0, re-evaluated against the UPDATED tensor, gains nothing new
+    udp = T.udp_initial_condition(args, init[0], lb, ub)
+    assert udp.fitness(cx[1])[0] == cf[1][0]
