@@ -152,6 +152,8 @@ def workload_config(args, pop_total):
                         f"rtol=atol=1e-12, 6048 samples, covered-space + penalties + collision fitness (enum 9)",
             "mesh": args.mesh, "population": pop_total, "pop_per_gpu": args.pop_per_gpu, "maneuvers": N_MAN,
             "chromosomes": "init-like, seed 1005 (SURVEY.md 8d)", "parallelism": f"islands x{args.gpus}",
+            "collided_trajectories": "retired at the first event point inside the mesh (fitness 1e30 either way); "
+                                     "reference arm and cpu_baseline integrate them to final_time like the reference",
             "l2": "256 MiB buffer overwritten between steps (inside the timed region; < 0.02 % of a step)"}
 
 
@@ -175,7 +177,9 @@ def run_ours(args):
     F = len(f)
     ctx.upload_mesh(v, f, 533.0)
     ctx.upload_grid(*O.default_grid())
-    p = N.make_params()
+    # collided trajectories score the constant 1e30: the path retires them at the first event point inside the mesh
+    # (identical fitness vector; the reference arm / cpu_baseline integrate them to the end, as the reference does)
+    p = N.make_params(stop_on_collision=1)
     pop_total = args.pop_per_gpu * world
     xs_all = init_like_population(pop_total, N_MAN, 1005)
     lo, hi = rank * args.pop_per_gpu, (rank + 1) * args.pop_per_gpu

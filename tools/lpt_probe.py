@@ -6,7 +6,7 @@ from oracle import oracle as O
 from bench import init_like_population, FIXED_POS
 mesh = sys.argv[1] if len(sys.argv) > 1 else "lp"
 c = N.Context(0); v, f = O.load_mesh(mesh); c.upload_mesh(v, f, 533.0); c.upload_grid(*O.default_grid())
-p = N.make_params()
+p = N.make_params(stop_on_collision=int(sys.argv[3]) if len(sys.argv) > 3 else 0)
 for pop in [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else (4096, 32768):
     xs = torch.from_numpy(init_like_population(pop, 2, 1005)).cuda()
     c.integrate(p, xs, FIXED_POS, 2, 2048); torch.cuda.synchronize()

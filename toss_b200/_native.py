@@ -300,6 +300,12 @@ class Context:
                                     self._stream()))
         return PropagationResult(self, ws, L, pop, n_man, knot_cap)
 
+    def collision_verdict(self, params: TossParams, prop: "PropagationResult"):
+        """re-derives collision flags / event counts from the stored knots (the stepper already computed them inline)"""
+        _check(lib().toss_collision_verdict(self.h, C.byref(params), prop.ws.data_ptr(), prop.pop, prop.n_man,
+                                            prop.knot_cap, self._stream()))
+        return prop
+
     def num_samples(self, params: TossParams) -> int:
         return int(lib().toss_num_samples(C.byref(params)))
 

@@ -225,10 +225,9 @@ int toss_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int p
 {
     TOSS_REQUIRE(ctx && p && d_workspace && (d_x || dim == 0), "toss_propagate: NULL argument");
     TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
-    if (int rc = launch_propagate(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_workspace, knot_cap,
-                                  (cudaStream_t)stream))
-        return rc;
-    return launch_collision(ctx, p, d_workspace, pop, n_man, knot_cap, (cudaStream_t)stream);
+    // the stepper ray-casts every event point while it sweeps the faces: the verdict is already in the workspace
+    return launch_propagate(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_workspace, knot_cap,
+                            (cudaStream_t)stream);
 }
 
 int toss_integrate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
@@ -333,7 +332,6 @@ int toss_population_fitness(toss_ctx *ctx, const toss_params *p, const double *d
     TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = launch_propagate(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_workspace, knot_cap, st)) return rc;
-    if (int rc = launch_collision(ctx, p, d_workspace, pop, n_man, knot_cap, st)) return rc;
     return launch_fitness_knots(ctx, p, d_workspace, pop, n_man, knot_cap, d_fitness, d_collision, d_counters,
                                 d_n_visited, st);
 }

@@ -41,7 +41,7 @@ constexpr int kK2Warps = K2_WARPS;
 constexpr int kK2Threads = kK2Warps * 32;
 constexpr int kK2Stages = K2_STAGES;
 constexpr int kK2Unroll = K2_UNROLL;
-constexpr int kK2BarSlots = 2 * K2_STAGES + 2;   // full[] | empty[] | live counter | pad
+constexpr int kK2BarSlots = 2 * K2_STAGES + 2 + (K2_STAGES + 2) / 2;   // full[] | empty[] | live + claim[] (ints) | pad
 constexpr int kSoaTileBytes = kSoaTileDoubles * 8;
 
 struct StepArgs {
@@ -64,6 +64,26 @@ struct StepArgs {
 // per-warp shared state (doubles): y[6] | k[13][6] | meta[2] | seg_t[n_man+2] | dv[3*n_man]
 __host__ __device__ inline int warp_state_doubles(int n_man) { return 6 + 78 + 2 + (n_man + 2) + 3 * (n_man > 0 ? n_man : 1); }
 
+// Called by lane 0 of a warp right after it arrived on empty[s] for tile `it`: if that arrival completed the phase
+// (every warp still in the ring has released the tile), claim the refill and issue the TMA load of tile it + stages.
+__device__ __forceinline__ void refill_if_released(uint64_t *bars, int *claim, double *mesh, const double *face_tiles,
+                                                   int n_tiles, int s, uint32_t it)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(&bars[kK2Stages + s])), "r"((it / kK2Stages) & 1u)
+        : "memory");
+    if (done && atomicMax(&claim[s], (int)it) < (int)it) {
+        mbar_arrive_expect_tx(&bars[s], kSoaTileBytes);
+        tma_load_1d(mesh + (size_t)s * kSoaTileDoubles,
+                    face_tiles + (size_t)((it + kK2Stages) % (uint32_t)n_tiles) * kSoaTileDoubles, kSoaTileBytes, &bars[s]);
+    }
+}
+
 template <bool kStream>
 __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const StepArgs a)
 {
@@ -78,6 +98,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     int *live = reinterpret_cast<int *>(bars + 2 * kK2Stages);   // warps that have not retired yet (STREAM)
     if (tid == 0) {
         *live = kK2Warps;
+        for (int s = 0; s < kK2Stages; ++s) live[1 + s] = -1;
         if (kStream) {
             for (int s = 0; s < kK2Stages; ++s) {
                 mbar_init(&bars[s], 1);
@@ -89,14 +110,13 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         mbar_fence_init();
     }
     __syncthreads();
-    uint32_t issued = 0;      // tiles issued by the producer thread (tid 0), STREAM only
+    int *claim = live + 1;    // claim[s] = newest tile of stage s whose refill has been issued (STREAM)
     if (tid == 0) {
         if (kStream) {
             for (int s = 0; s < kK2Stages; ++s) {   // the ring is cyclic over the mesh: always something to fetch
                 mbar_arrive_expect_tx(&bars[s], kSoaTileBytes);
                 tma_load_1d(mesh + (size_t)s * kSoaTileDoubles,
-                            a.face_tiles + (size_t)(issued % a.n_tiles) * kSoaTileDoubles, kSoaTileBytes, &bars[s]);
-                ++issued;
+                            a.face_tiles + (size_t)(s % a.n_tiles) * kSoaTileDoubles, kSoaTileBytes, &bars[s]);
             }
         } else {
             const uint32_t bytes = (uint32_t)mesh_doubles * 8u;
@@ -119,10 +139,14 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     // warp-uniform trajectory state
     bool active = false, queue_empty = false, counted_out = false;
     int traj = -1, stage = 0, seg = 0, nseg = 0, nk = 0, steps = 0, clipped = 0, after_accept = 0, status = 0;
-    int n_acc = 0, n_rej = 0, n_ev = 0;
+    int n_acc = 0, n_rej = 0, n_ev = 0, collided = 0, stopped = 0, ray_sweep = 0;
     long long n_rhs = 0;
     double t = 0.0, dt = 0.0, tf = 0.0;
 
+#ifdef K2_PROFILE
+    long long prof_wait = 0, prof_comp = 0, prof_wait0 = 0, prof_idle = 0;
+    const long long prof_t0 = clock64();
+#endif
     for (;;) {
         // ------------------------------------------------ fetch a trajectory, decode the chromosome
         if (!active && !queue_empty) {
@@ -195,7 +219,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 clipped = 0;
                 after_accept = 0;
                 status = 0;
-                n_acc = n_rej = n_ev = 0;
+                n_acc = n_rej = n_ev = collided = stopped = ray_sweep = 0;
                 n_rhs = 0;
                 if (lane == 0) a.seg_start[(size_t)traj * (a.n_man + 2)] = 0;
             }
@@ -215,7 +239,12 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                         mbar_wait(&bars[kK2Stages + s], (last / kK2Stages) & 1u);
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_drop(&bars[kK2Stages + s]);
+                    if (lane == 0) {
+                        // the phase this arrival belongs to: the first tile >= tile_it that lives in stage s
+                        const uint32_t nxt = tile_it + (uint32_t)((s + kK2Stages - (int)(tile_it % kK2Stages)) % kK2Stages);
+                        mbar_arrive_drop(&bars[kK2Stages + s]);
+                        refill_if_released(bars, claim, mesh, a.face_tiles, a.n_tiles, s, nxt);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) atomicSub(live, 1);
@@ -249,23 +278,36 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         if (active && p.activate_rotation)
             rotate_point_dev(te, qx, qy, qz, a.axis.x, a.axis.y, a.axis.z, p.spin_velocity, Px, Py, Pz);
 
+        // A sweep is either a gravity evaluation or (ray_sweep) the point-in-polyhedron test of an event point:
+        // compute_trajectory.py:264-282 records every ACCEPTED state inside the risk sphere, is_outside
+        // (mesh_utility.py:70-89) ray-casts it.  Event points are rare (a few per close pass), so the test gets a
+        // sweep of its own over the same tile stream instead of loading the hot loop's registers.
+        int hits = 0;
+
         // ------------------------------------------------ gravity sweep over all faces
         double ax = 0.0, ay = 0.0, az = 0.0, pv = 0.0;
         if (kStream) {
             for (int tl = 0; tl < a.n_tiles; ++tl, ++tile_it) {
                 const int s = tile_it % kK2Stages;
-                if (tid == 0 && tile_it >= 1) {   // refill the stage released one tile ago
-                    const uint32_t prev = tile_it - 1;
-                    const int ps = prev % kK2Stages;
-                    mbar_wait(&bars[kK2Stages + ps], (prev / kK2Stages) & 1u);
-                    mbar_arrive_expect_tx(&bars[ps], kSoaTileBytes);
-                    tma_load_1d(mesh + (size_t)ps * kSoaTileDoubles,
-                                a.face_tiles + (size_t)(issued % a.n_tiles) * kSoaTileDoubles, kSoaTileBytes,
-                                &bars[ps]);
-                    ++issued;
-                }
+#ifdef K2_PROFILE
+                const long long c0 = clock64();
+#endif
                 mbar_wait(&bars[s], (tile_it / kK2Stages) & 1u);
-                if (active) {
+#ifdef K2_PROFILE
+                const long long c1 = clock64();
+                prof_wait += c1 - c0;
+                if (tl == 0) prof_wait0 += c1 - c0;
+                if (!active) prof_idle += c1 - c0;
+#endif
+                if (active && ray_sweep) {
+                    const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
+                    for (int f = 0; f < kSoaTileFaces; f += 32) {
+                        const double *col = tile + f;
+                        hits += ray_hits_dev(qx, qy, qz, col[0], col[kSoaTileFaces], col[2 * kSoaTileFaces],
+                                             col[3 * kSoaTileFaces], col[4 * kSoaTileFaces], col[5 * kSoaTileFaces],
+                                             col[6 * kSoaTileFaces], col[7 * kSoaTileFaces], col[8 * kSoaTileFaces]);
+                    }
+                } else if (active) {
                     const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
 #pragma unroll kK2Unroll
                     for (int f = 0; f < kSoaTileFaces; f += 32) {
@@ -274,17 +316,40 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bars[kK2Stages + s]);
+#ifdef K2_PROFILE
+                if (active) prof_comp += clock64() - c1;
+#endif
+                // release the stage; the warp whose arrival completes the phase (the last one out) refills it at
+                // once -- no dedicated producer, no warp ever waits on another one's bookkeeping
+                if (lane == 0) {
+                    mbar_arrive(&bars[kK2Stages + s]);
+                    refill_if_released(bars, claim, mesh, a.face_tiles, a.n_tiles, s, tile_it);
+                }
             }
         } else {
             const int Fp = a.Fpad32;
+            if (ray_sweep) {
+                for (int f = lane; f < Fp; f += 32) {
+                    const double *col = mesh + f;
+                    hits += ray_hits_dev(qx, qy, qz, col[0], col[Fp], col[2 * Fp], col[3 * Fp], col[4 * Fp], col[5 * Fp],
+                                         col[6 * Fp], col[7 * Fp], col[8 * Fp]);
+                }
+            } else {
 #pragma unroll kK2Unroll
-            for (int f = lane; f < Fp; f += 32) {
-                const double *col = mesh + f;
-                face_term<false>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, ax, ay, az, pv);
+                for (int f = lane; f < Fp; f += 32) {
+                    const double *col = mesh + f;
+                    face_term<false>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, ax, ay, az, pv);
+                }
             }
         }
         if (!active) continue;
+        bool post_event = false;   // run the tail of the stage-0 logic (after the event test, if there was one)
+        if (ray_sweep) {
+            ray_sweep = 0;
+            ++n_ev;
+            if (__reduce_add_sync(0xffffffffu, hits) & 1) collided = 1;   // odd number of +z hits: inside the mesh
+            post_event = true;
+        } else {
         ax = warp_sum(ax);
         ay = warp_sum(ay);
         az = warp_sum(az);
@@ -297,8 +362,6 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         else if (lane == 5) kc = -(a.Grho * az);
         if (lane < 6) sk[6 * stage + lane] = kc;
         __syncwarp();
-
-        // ------------------------------------------------ advance the state machine
         if (stage == 0) {
             // f0 at a segment start or at a freshly accepted state: this is a knot
             if (nk >= a.knot_cap) {
@@ -312,12 +375,31 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 }
                 ++nk;
             }
+            if (status == 0 && after_accept && p.activate_event &&
+                add_(add_(mul_(qx, qx), mul_(qy, qy)), mul_(qz, qz)) <= R2) {
+                ray_sweep = 1;   // event point: next sweep is its ray cast, then the logic below resumes
+                continue;
+            }
+            post_event = true;
+        }
+        }
+
+        // ------------------------------------------------ advance the state machine
+        if (post_event) {
             if (after_accept) {
                 after_accept = 0;
-                ++steps;
-                if (steps > p.max_steps) status = 1;
+                // a collided trajectory scores the constant 1e30 (udp_initial_condition.py:126-128): with
+                // stop_on_collision it retires here; the reference behaviour (0) integrates on to final_time
+                if (collided && p.stop_on_collision) {
+                    stopped = 1;
+                } else {
+                    ++steps;
+                    if (steps > p.max_steps) status = 1;
+                }
             }
-            if (status == 0 && !(t < tf)) {   // segment finished
+            if (stopped) {
+                // fall through to retirement
+            } else if (status == 0 && !(t < tf)) {   // segment finished
                 ++seg;
                 if (seg >= nseg) {
                     active = false;
@@ -395,21 +477,37 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         active = false;
         if (lane == 0) {
             a.seg_start[(size_t)traj * (a.n_man + 2) + (seg < nseg ? seg + 1 : nseg)] = nk;
-            if (status != 0) a.n_seg[traj] = seg < nseg ? seg + 1 : nseg;
+            if (status != 0 || stopped) a.n_seg[traj] = seg < nseg ? seg + 1 : nseg;
             toss_counters c;
             c.n_rhs = n_rhs;
             c.n_accepted = n_acc;
             c.n_rejected = n_rej;
-            c.n_event_points = 0;
+            c.n_event_points = n_ev;
             c.status = status;
             a.counters[traj] = c;
-            a.collision[traj] = 0;
+            a.collision[traj] = collided;
         }
     }
 
+#ifdef K2_PROFILE
+    if (lane == 0) {
+        unsigned long long *pr = reinterpret_cast<unsigned long long *>(a.queue) + 2;   // queue[4..] (LPT area, unused here)
+        atomicAdd(pr + 0, (unsigned long long)prof_wait);
+        atomicAdd(pr + 1, (unsigned long long)prof_comp);
+        atomicAdd(pr + 2, (unsigned long long)(clock64() - prof_t0));
+        atomicAdd(pr + 3, 1ULL);
+        atomicAdd(pr + 4, (unsigned long long)prof_wait0);
+        atomicAdd(pr + 5, (unsigned long long)prof_idle);
+        atomicAdd(pr + 8 + (wid & 7), (unsigned long long)prof_wait);
+        atomicAdd(pr + 16 + (wid & 7), (unsigned long long)prof_comp);
+    }
+#endif
     // drain the TMA copies still in flight before the CTA's shared memory goes away
     if (kStream && tid == 0) {
-        for (uint32_t it = tile_it; it < issued; ++it) mbar_wait(&bars[it % kK2Stages], (it / kK2Stages) & 1u);
+        // (every tile below tile_it + kK2Stages has been issued: the stage of tile i is refilled with tile i + stages
+        //  by whoever releases it last, and this warp has released all tiles below tile_it)
+        for (uint32_t it = tile_it; it < tile_it + kK2Stages; ++it)
+            mbar_wait(&bars[it % kK2Stages], (it / kK2Stages) & 1u);
     }
 }
 
@@ -591,7 +689,7 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     a.collision = reinterpret_cast<int32_t *>(ws + L.collision);
     a.queue = reinterpret_cast<int32_t *>(ws + L.queue);
     a.counters = reinterpret_cast<toss_counters *>(ws + L.counters);
-    TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 16, st));
+    TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
     // longest-processing-time-first: with ~1.7 trajectories per warp slot and a 4x spread of trajectory lengths the
     // tail of an index-ordered queue costs ~40 %; a cheap point-mass pre-integration predicts the step counts.
     a.order = nullptr;

@@ -77,7 +77,10 @@ class udp_initial_condition:
             raise ValueError(f"len(initial_condition) + len(chromosome) = {fixed.size + xs.shape[1]}, "
                              f"expected 7 + 5*number_of_maneuvers = {7 + 5 * n_man}")
         ctx = context_for_args(args, need_grid=True)
-        p = params_from_args(args)
+        # a collided trajectory scores the constant 1e30 whatever happens afterwards, so the batch path retires it at
+        # the first event point found inside the mesh (same fitness vector, fewer gravity evaluations); the
+        # compute_trajectory API keeps the reference behaviour and integrates to final_time
+        p = params_from_args(args, stop_on_collision=1)
         lo, hi = shard_bounds(len(xs))
         local = ctx.population_fitness_host(p, xs[lo:hi], fixed, n_man, self.knot_capacity) if hi > lo else None
         if local is not None and (local["counters"]["status"] == 3).any():
