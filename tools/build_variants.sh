@@ -9,8 +9,7 @@ build() { # name flags...
   grep -A2 "stepper_kernelILb1" ../../build/variants/$name.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name"
 }
 build base
-build w16u1 -DK2_WARPS=16 -DK2_MINBLOCKS=1 -DK2_STAGES=6 -DK2_UNROLL=1
-build t256w16 -DSOA_TILE_FACES=256 -DK2_WARPS=16 -DK2_MINBLOCKS=1 -DK2_STAGES=3
-build t512w16 -DSOA_TILE_FACES=512 -DK2_WARPS=16 -DK2_MINBLOCKS=1 -DK2_STAGES=2
-build t256w8 -DSOA_TILE_FACES=256 -DK2_WARPS=8 -DK2_MINBLOCKS=2 -DK2_STAGES=2
-build t256w16u4 -DSOA_TILE_FACES=256 -DK2_WARPS=16 -DK2_MINBLOCKS=1 -DK2_STAGES=3 -DK2_UNROLL=4
+build u1 -DK2_UNROLL=1
+build w16u1 -DK2_WARPS=16 -DK2_MINBLOCKS=1 -DK2_STAGES=4 -DK2_UNROLL=1
+build w16 -DK2_WARPS=16 -DK2_MINBLOCKS=1 -DK2_STAGES=4
+build st2 -DK2_STAGES=2

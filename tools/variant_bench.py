@@ -10,7 +10,7 @@ from oracle import oracle as O
 from bench import init_like_population, FIXED_POS
 mesh, pop = sys.argv[1], int(sys.argv[2])
 c = N.Context(0); v, f = O.load_mesh(mesh); c.upload_mesh(v, f, 533.0); c.upload_grid(*O.default_grid())
-p = N.make_params(); xs = torch.from_numpy(init_like_population(pop, 2, 1005)).cuda()
+p = N.make_params(stop_on_collision=1); xs = torch.from_numpy(init_like_population(pop, 2, 1005)).cuda()
 c.integrate(p, xs, FIXED_POS, 2, 2048); torch.cuda.synchronize()
 best = 1e9
 for _ in range(3):

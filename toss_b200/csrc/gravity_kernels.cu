@@ -13,7 +13,8 @@ constexpr int kAosTileBytes = kAosTileFaces * kAosStride * 8;
 
 template <bool kPot>
 __global__ void __launch_bounds__(kK1Threads, 4)
-gravity_points_kernel(const double *__restrict__ face_aos, int n_tiles, const double *__restrict__ pts, int64_t n,
+gravity_points_kernel(const double *__restrict__ face_aos, int n_tiles, int last_tile_faces,
+                      const double *__restrict__ pts, int64_t n,
                       double *__restrict__ acc, double *__restrict__ pot, double Grho)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -60,8 +61,9 @@ gravity_points_kernel(const double *__restrict__ face_aos, int n_tiles, const do
         }
         mbar_wait(&full[s], ph);
         const double *tile = tiles + (size_t)s * kAosTileFaces * kAosStride;
+        const int f_end = (it == n_tiles - 1) ? last_tile_faces : kAosTileFaces;   // skip the padding records
 #pragma unroll 2
-        for (int f = 0; f < kAosTileFaces; ++f) {
+        for (int f = 0; f < f_end; ++f) {
             const double *rec = tile + f * kAosStride;
             face_term<kPot>([rec](int k) { return rec[k]; }, Px, Py, Pz, ax, ay, az, pv);
         }
@@ -283,13 +285,15 @@ int launch_gravity(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc,
         if (d_pot) {
             TOSS_CHECK_CUDA(cudaFuncSetAttribute(gravity_points_kernel<true>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gravity_points_kernel<true><<<(unsigned)blocks, kK1Threads, smem, st>>>(ctx->d_face_aos, ctx->n_aos_tiles,
-                                                                                  d_pts, n, d_acc, d_pot, ctx->Grho);
+            gravity_points_kernel<true><<<(unsigned)blocks, kK1Threads, smem, st>>>(
+                ctx->d_face_aos, ctx->n_aos_tiles, ctx->F - (ctx->n_aos_tiles - 1) * kAosTileFaces, d_pts, n, d_acc, d_pot,
+                ctx->Grho);
         } else {
             TOSS_CHECK_CUDA(cudaFuncSetAttribute(gravity_points_kernel<false>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gravity_points_kernel<false><<<(unsigned)blocks, kK1Threads, smem, st>>>(
-                ctx->d_face_aos, ctx->n_aos_tiles, d_pts, n, d_acc, nullptr, ctx->Grho);
+                ctx->d_face_aos, ctx->n_aos_tiles, ctx->F - (ctx->n_aos_tiles - 1) * kAosTileFaces, d_pts, n, d_acc, nullptr,
+                ctx->Grho);
         }
     }
     ctx->launches++;

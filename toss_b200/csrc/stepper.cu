@@ -50,7 +50,7 @@ struct StepArgs {
     double Grho;
     const double *face_soa;    // [25][Fpad32]           (RESIDENT)
     const double *face_tiles;  // [n_tiles][25][128]     (STREAM)
-    int Fpad32, n_tiles;
+    int Fpad32, n_tiles, last_tile_faces;   // last_tile_faces: real faces of the last tile rounded up to 32
     const double *x;           // pop x dim
     int pop, dim, n_fixed, n_man, knot_cap;
     double fixed[8];
@@ -289,6 +289,8 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         if (kStream) {
             for (int tl = 0; tl < a.n_tiles; ++tl, ++tile_it) {
                 const int s = tile_it % kK2Stages;
+                // rows of 32 faces in this tile that hold real faces (the last tile is only partly filled)
+                const int f_end = (tl == a.n_tiles - 1) ? a.last_tile_faces : kSoaTileFaces;
 #ifdef K2_PROFILE
                 const long long c0 = clock64();
 #endif
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 #endif
                 if (active && ray_sweep) {
                     const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
-                    for (int f = 0; f < kSoaTileFaces; f += 32) {
+                    for (int f = 0; f < f_end; f += 32) {
                         const double *col = tile + f;
                         hits += ray_hits_dev(qx, qy, qz, col[0], col[kSoaTileFaces], col[2 * kSoaTileFaces],
                                              col[3 * kSoaTileFaces], col[4 * kSoaTileFaces], col[5 * kSoaTileFaces],
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 } else if (active) {
                     const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
 #pragma unroll kK2Unroll
-                    for (int f = 0; f < kSoaTileFaces; f += 32) {
+                    for (int f = 0; f < f_end; f += 32) {
                         const double *col = tile + f;
                         face_term<false>([col](int k) { return col[k * kSoaTileFaces]; }, Px, Py, Pz, ax, ay, az, pv);
                     }
@@ -673,6 +675,7 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     a.face_tiles = ctx->d_face_tiles;
     a.Fpad32 = ctx->Fpad32;
     a.n_tiles = ctx->n_soa_tiles;
+    a.last_tile_faces = ctx->Fpad32 - (ctx->n_soa_tiles - 1) * kSoaTileFaces;
     a.x = d_x;
     a.pop = pop;
     a.dim = dim;
