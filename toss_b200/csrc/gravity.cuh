@@ -20,9 +20,9 @@
 
 // One face, one field point P.  fld(k) returns field k of the face record (common.cuh layout); the
 // accessor decides where it comes from (shared-memory AoS broadcast, shared-memory SoA, global SoA).
-template <bool kPot, class Fld>
-__device__ __forceinline__ void face_term(Fld fld, double Px, double Py, double Pz, double &ax, double &ay,
-                                          double &az, double &pot)
+// S_p of one face (the scalar that multiplies N_p); hp_out = signed plane distance (potential term).
+template <class Fld>
+__device__ __forceinline__ double face_S(Fld fld, double Px, double Py, double Pz, double &hp_out)
 {
     const double r0x = fld(0) - Px, r0y = fld(1) - Py, r0z = fld(2) - Pz;
     const double r1x = fld(3) - Px, r1y = fld(4) - Py, r1z = fld(5) - Pz;
@@ -67,10 +67,20 @@ __device__ __forceinline__ void face_term(Fld fld, double Px, double Py, double 
         ln2 = tm_two_atanh(tm_div(G2, A2));
         om = 2.0 * tm_atan2(num, den);
     }
-    const double S = fma(-hp, om, fma(hq2, ln2, fma(hq1, ln1, hq0 * ln0)));
-    ax = fma(Nx, S, ax);
-    ay = fma(Ny, S, ay);
-    az = fma(Nz, S, az);
+    hp_out = hp;
+    return fma(-hp, om, fma(hq2, ln2, fma(hq1, ln1, hq0 * ln0)));
+}
+
+// One face, one field point: acc += N_p S_p (and pot += hp S_p).
+template <bool kPot, class Fld>
+__device__ __forceinline__ void face_term(Fld fld, double Px, double Py, double Pz, double &ax, double &ay,
+                                          double &az, double &pot)
+{
+    double hp;
+    const double S = face_S(fld, Px, Py, Pz, hp);
+    ax = fma(fld(9), S, ax);
+    ay = fma(fld(10), S, ay);
+    az = fma(fld(11), S, az);
     if (kPot) pot = fma(hp, S, pot);
 }
 

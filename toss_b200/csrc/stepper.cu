@@ -84,16 +84,36 @@ __device__ __forceinline__ void refill_if_released(uint64_t *bars, int *claim, d
     }
 }
 
-template <bool kStream>
+// Teams (kTeam = 2 or 4 warps per trajectory) are for populations too small to fill the machine with one warp
+// each (or to keep its tail short).  The owner warp (rank 0) runs the state machine; every warp of the team computes
+// the per-face scalar S_p for its share of the 32-face rows of a tile (rows rank, rank + kTeam, ...) into a shared
+// buffer; after a team barrier the owner adds N_p S_p in the canonical order (row 0, 1, 2, ... of every tile).  The
+// arithmetic, and therefore every result bit, is the same for any team size.
+enum : int { kModeGrav = 0, kModeSkip = 1, kModeRetire = 2 };
+constexpr int kTeamBufDoubles = 4 + 2 * 4 * 32;   // P[3] + mode | S[2 buffers][4 rows][32 lanes]
+
+__device__ __forceinline__ void team_bar(int team, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(nthreads) : "memory");
+}
+
+template <bool kStream, int kTeam>
 __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int team = wid / kTeam, rank = wid % kTeam;
     const int mesh_doubles = kStream ? kK2Stages * kSoaTileDoubles : kFaceFields * a.Fpad32;
     double *mesh = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(mesh + mesh_doubles);   // full[3] empty[3] (STREAM) / full[1]
     double *wstate = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)wid * warp_state_doubles(a.n_man);
     double *sy = wstate, *sk = wstate + 6, *meta = wstate + 84, *seg_t = wstate + 86, *sdv = seg_t + (a.n_man + 2);
+    double *tbuf = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)kK2Warps * warp_state_doubles(a.n_man) +
+                   (size_t)team * kTeamBufDoubles;                       // team mailbox: P, mode, S buffers
+    volatile double *tP = tbuf;
+    volatile int *tmode = reinterpret_cast<volatile int *>(tbuf + 3);
+    double *sbuf = tbuf + 4;
+    int spar = 0;                                                        // which S buffer the current tile uses
 
     int *live = reinterpret_cast<int *>(bars + 2 * kK2Stages);   // warps that have not retired yet (STREAM)
     if (tid == 0) {
@@ -133,6 +153,70 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     if (!kStream) mbar_wait(&bars[0], 0);
 
     const toss_params &p = a.p;
+    if (kTeam > 1 && rank != 0) {
+        // ------------------------------------------------ helper warp: an S_p server for its team's owner
+        uint32_t it = 0;
+        for (;;) {
+            team_bar(team, 32 * kTeam);   // the owner has published the evaluation point and the mode
+            const int mode = *tmode;
+            const double Px = tP[0], Py = tP[1], Pz = tP[2];
+            if (mode == kModeRetire) {
+                if (kStream) {
+                    for (int s = 0; s < kK2Stages; ++s) {
+                        if (it > (uint32_t)s) {
+                            const uint32_t last = it - 1 - ((it - 1 - s) % kK2Stages);
+                            mbar_wait(&bars[kK2Stages + s], (last / kK2Stages) & 1u);
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            const uint32_t nxt = it + (uint32_t)((s + kK2Stages - (int)(it % kK2Stages)) % kK2Stages);
+                            mbar_arrive_drop(&bars[kK2Stages + s]);
+                            refill_if_released(bars, claim, mesh, a.face_tiles, a.n_tiles, s, nxt);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) atomicSub(live, 1);
+                }
+                return;
+            }
+            if (kStream) {
+                for (int tl = 0; tl < a.n_tiles; ++tl, ++it) {
+                    const int s = it % kK2Stages;
+                    const int rows = ((tl == a.n_tiles - 1) ? a.last_tile_faces : kSoaTileFaces) >> 5;
+                    mbar_wait(&bars[s], (it / kK2Stages) & 1u);
+                    if (mode == kModeGrav) {
+                        const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
+                        for (int r = rank; r < rows; r += kTeam) {
+                            const double *col = tile + 32 * r;
+                            double hp;
+                            sbuf[(spar * 4 + r) * 32 + lane] =
+                                face_S([col](int k) { return col[k * kSoaTileFaces]; }, Px, Py, Pz, hp);
+                        }
+                        team_bar(team, 32 * kTeam);   // S of this tile complete; the owner accumulates
+                        spar ^= 1;
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&bars[kK2Stages + s]);
+                        refill_if_released(bars, claim, mesh, a.face_tiles, a.n_tiles, s, it);
+                    }
+                }
+            } else if (mode == kModeGrav) {
+                const int Fp = a.Fpad32, rows_total = Fp >> 5;
+                for (int v = 0; v * 4 < rows_total; ++v) {
+                    const int rows = rows_total - 4 * v < 4 ? rows_total - 4 * v : 4;
+                    for (int r = rank; r < rows; r += kTeam) {
+                        const double *col = mesh + 32 * (4 * v + r) + lane;
+                        double hp;
+                        sbuf[(spar * 4 + r) * 32 + lane] = face_S([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, hp);
+                    }
+                    team_bar(team, 32 * kTeam);
+                    spar ^= 1;
+                }
+            }
+        }
+    }
+    bool team_alive = kTeam > 1;   // helpers still listening (owner side)
     const double R2 = mul_(p.radius_inner, p.radius_inner);
     uint32_t tile_it = 0;     // tiles consumed so far by this warp (== by every warp: lock step)
 
@@ -230,6 +314,12 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
             // arrive_drop on each `empty` barrier (counts as this warp's arrival for the tile it will not
             // read and removes it from all later phases).  Warp 0 owns the producer thread: it stays as an
             // idle consumer/producer until the other warps are gone.
+            if (team_alive) {   // dissolve the team: the helpers leave (and drop out of the tile ring) on their own
+                team_alive = false;
+                if (lane == 0) *tmode = kModeRetire;
+                __syncwarp();
+                team_bar(team, 32 * kTeam);
+            }
             if (!kStream) break;
             if (wid != 0) {
                 for (int s = 0; s < kK2Stages; ++s) {
@@ -278,6 +368,16 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         if (active && p.activate_rotation)
             rotate_point_dev(te, qx, qy, qz, a.axis.x, a.axis.y, a.axis.z, p.spin_velocity, Px, Py, Pz);
 
+        if (team_alive) {   // tell the helpers what this sweep is
+            if (lane == 0) {
+                tP[0] = Px;
+                tP[1] = Py;
+                tP[2] = Pz;
+                *tmode = ray_sweep ? kModeSkip : kModeGrav;
+            }
+            __syncwarp();
+            team_bar(team, 32 * kTeam);
+        }
         // A sweep is either a gravity evaluation or (ray_sweep) the point-in-polyhedron test of an event point:
         // compute_trajectory.py:264-282 records every ACCEPTED state inside the risk sphere, is_outside
         // (mesh_utility.py:70-89) ray-casts it.  Event points are rare (a few per close pass), so the test gets a
@@ -309,6 +409,25 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                                              col[3 * kSoaTileFaces], col[4 * kSoaTileFaces], col[5 * kSoaTileFaces],
                                              col[6 * kSoaTileFaces], col[7 * kSoaTileFaces], col[8 * kSoaTileFaces]);
                     }
+                } else if (active && kTeam > 1) {
+                    // team sweep: S_p of my rows into the buffer, barrier, then N_p S_p of ALL rows in canonical order
+                    const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
+                    const int rows = f_end >> 5;
+                    for (int r = 0; r < rows; r += kTeam) {
+                        const double *col = tile + 32 * r;
+                        double hp;
+                        sbuf[(spar * 4 + r) * 32 + lane] =
+                            face_S([col](int k) { return col[k * kSoaTileFaces]; }, Px, Py, Pz, hp);
+                    }
+                    team_bar(team, 32 * kTeam);
+                    for (int r = 0; r < rows; ++r) {
+                        const double *col = tile + 32 * r;
+                        const double S = sbuf[(spar * 4 + r) * 32 + lane];
+                        ax = fma(col[9 * kSoaTileFaces], S, ax);
+                        ay = fma(col[10 * kSoaTileFaces], S, ay);
+                        az = fma(col[11 * kSoaTileFaces], S, az);
+                    }
+                    spar ^= 1;
                 } else if (active) {
                     const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
 #pragma unroll kK2Unroll
@@ -335,6 +454,25 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     const double *col = mesh + f;
                     hits += ray_hits_dev(qx, qy, qz, col[0], col[Fp], col[2 * Fp], col[3 * Fp], col[4 * Fp], col[5 * Fp],
                                          col[6 * Fp], col[7 * Fp], col[8 * Fp]);
+                }
+            } else if (kTeam > 1) {
+                const int rows_total = Fp >> 5;
+                for (int v = 0; v * 4 < rows_total; ++v) {
+                    const int rows = rows_total - 4 * v < 4 ? rows_total - 4 * v : 4;
+                    for (int r = 0; r < rows; r += kTeam) {
+                        const double *col = mesh + 32 * (4 * v + r) + lane;
+                        double hp;
+                        sbuf[(spar * 4 + r) * 32 + lane] = face_S([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, hp);
+                    }
+                    team_bar(team, 32 * kTeam);
+                    for (int r = 0; r < rows; ++r) {
+                        const double *col = mesh + 32 * (4 * v + r) + lane;
+                        const double S = sbuf[(spar * 4 + r) * 32 + lane];
+                        ax = fma(col[9 * Fp], S, ax);
+                        ay = fma(col[10 * Fp], S, ay);
+                        az = fma(col[11 * Fp], S, az);
+                    }
+                    spar ^= 1;
                 }
             } else {
 #pragma unroll kK2Unroll
@@ -705,22 +843,38 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
         a.order = order;
     }
 
-    const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8;
+    // warps per trajectory: one when the population fills the machine several times over; two or four below that,
+    // which shortens the tail (trajectory lengths spread 4x) and fills the SMs of small populations.  Results do
+    // not depend on it.
+    const int slots = K2_MINBLOCKS * ctx->sm_count * kK2Warps;
+    int team = pop >= 6 * slots ? 1 : (2 * pop >= 3 * slots ? 2 : 4);
+    if (const char *e = getenv("TOSS_B200_TEAM")) team = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1);   // developer override
+    const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 +
+                               (size_t)kK2Warps * kTeamBufDoubles * 8;
     const size_t resident_bytes = (size_t)kFaceFields * ctx->Fpad32 * 8 + state_bytes;
     const size_t stream_bytes = (size_t)kK2Stages * kSoaTileBytes + state_bytes;
     const bool resident = resident_bytes <= (size_t)(200 / K2_MINBLOCKS) * 1024;   // every CTA on an SM keeps its own copy
-    int ctas = (pop + kK2Warps - 1) / kK2Warps;
+    const int per_cta = kK2Warps / team;
+    int ctas = (pop + per_cta - 1) / per_cta;
     const int max_ctas = K2_MINBLOCKS * ctx->sm_count;
     if (ctas > max_ctas) ctas = max_ctas;
+    const size_t smem = resident ? resident_bytes : stream_bytes;
+#define TOSS_LAUNCH_STEPPER(STREAM, TEAM)                                                                          \
+    do {                                                                                                           \
+        TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<STREAM, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                          \
+        stepper_kernel<STREAM, TEAM><<<ctas, kK2Threads, smem, st>>>(a);                                          \
+    } while (0)
     if (resident) {
-        TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)resident_bytes));
-        stepper_kernel<false><<<ctas, kK2Threads, resident_bytes, st>>>(a);
+        if (team == 1) TOSS_LAUNCH_STEPPER(false, 1);
+        else if (team == 2) TOSS_LAUNCH_STEPPER(false, 2);
+        else TOSS_LAUNCH_STEPPER(false, 4);
     } else {
-        TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)stream_bytes));
-        stepper_kernel<true><<<ctas, kK2Threads, stream_bytes, st>>>(a);
+        if (team == 1) TOSS_LAUNCH_STEPPER(true, 1);
+        else if (team == 2) TOSS_LAUNCH_STEPPER(true, 2);
+        else TOSS_LAUNCH_STEPPER(true, 4);
     }
+#undef TOSS_LAUNCH_STEPPER
     ctx->launches++;
     TOSS_CHECK_CUDA(cudaGetLastError());
     return 0;

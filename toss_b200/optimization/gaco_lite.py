@@ -14,7 +14,7 @@ import numpy as np
 
 
 class GacoLite:
-    def __init__(self, gen: int, ker: int = 13, q: float = 1.0, oracle: float = 1e9, acc: float = 0.0,
+    def __init__(self, gen: int, ker: int = 13, q: float = 1.0, oracle_parameter: float = 1e9, acc: float = 0.0,
                  threshold: int = 1, n_gen_mark: int = 7, impstop: int = 100000, evalstop: int = 100000,
                  focus: float = 0.0, memory: bool = False, seed: int = 0):
         self.gen, self.ker, self.q, self.n_gen_mark = int(gen), int(ker), float(q), int(n_gen_mark)
