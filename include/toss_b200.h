@@ -115,7 +115,8 @@ int toss_workspace_layout(int pop, int n_man, int knot_cap, toss_ws_layout *out)
 /* Replaces compute_trajectory(x, args, compute_motion) (compute_trajectory.py:13-162) for a population.
  * d_x: pop x dim decision vectors (row-major); h_fixed: the n_fixed leading values the UDP prepends
  * (udp_initial_condition.py:117-120; 0, 3 or 7).  n_fixed + dim must equal 7 + 5 n_man.
- * Fills the workspace (knots, segments, counters, collision flags). */
+ * Fills the workspace (knots, segments, counters, collision flags: every accepted state inside the risk sphere is
+ * ray-cast against the mesh by the stepper itself, compute_trajectory.py:141-159). */
 int toss_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim,
                    const double *h_fixed, int n_fixed, int n_man, void *d_workspace, int knot_cap,
                    uintptr_t stream);
