@@ -143,7 +143,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, pop_total):
@@ -317,7 +317,7 @@ def run_ours(args):
             line["gravity_microbench"] = gravity_microbench(ctx, F, fp64_peak)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(O, args, xs_all)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -359,7 +359,24 @@ def cpu_baseline(O, args, xs_all):
             "sample": f"first {sample} chromosomes of the same population, oracle/toss_oracle.c on {cores} pthreads, {dt:.1f} s"}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner with
+    printf), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
