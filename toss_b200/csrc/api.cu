@@ -39,7 +39,9 @@ static void free_mesh(toss_ctx *c)
     cudaFree(c->d_face_aos);
     cudaFree(c->d_face_soa);
     cudaFree(c->d_face_tiles);
-    c->d_face_aos = c->d_face_soa = c->d_face_tiles = nullptr;
+    cudaFree(c->d_mascons);
+    c->d_face_aos = c->d_face_soa = c->d_face_tiles = c->d_mascons = nullptr;
+    c->n_mascons = 0;
 }
 static void free_grid(toss_ctx *c)
 {
@@ -122,6 +124,54 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
         }
         ctx->GM = ctx->Grho * vol;
         for (int k = 0; k < 3; ++k) ctx->com[k] = vol != 0.0 ? c[k] / vol : 0.0;
+        // mascon proxy of the body (only used to ORDER the work queue): centres of an 8^3 grid over the bounding box
+        // that lie inside the mesh (+z ray parity), equal masses
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int v = 0; v < V; ++v)
+            for (int k = 0; k < 3; ++k) {
+                lo[k] = h_verts[3 * v + k] < lo[k] ? h_verts[3 * v + k] : lo[k];
+                hi[k] = h_verts[3 * v + k] > hi[k] ? h_verts[3 * v + k] : hi[k];
+            }
+        const int G = 8;
+        std::vector<double> mc;
+        for (int i = 0; i < G; ++i)
+            for (int j = 0; j < G; ++j)
+                for (int k = 0; k < G; ++k) {
+                    const double o[3] = {lo[0] + (i + 0.5) * (hi[0] - lo[0]) / G, lo[1] + (j + 0.5) * (hi[1] - lo[1]) / G,
+                                         lo[2] + (k + 0.5) * (hi[2] - lo[2]) / G};
+                    int hits = 0;
+                    for (int f = 0; f < F; ++f) {
+                        const double *a = h_verts + 3 * (size_t)h_faces[3 * f], *b = h_verts + 3 * (size_t)h_faces[3 * f + 1],
+                                     *d = h_verts + 3 * (size_t)h_faces[3 * f + 2];
+                        const double e1x = b[0] - a[0], e1y = b[1] - a[1], e1z = b[2] - a[2];
+                        const double e2x = d[0] - a[0], e2y = d[1] - a[1], e2z = d[2] - a[2];
+                        const double hx = -e2y, hy = e2x, det = e1x * hx + e1y * hy;
+                        if (det < 1e-6 && det > -1e-6) continue;
+                        const double inv = 1.0 / det, sx = o[0] - a[0], sy = o[1] - a[1], sz = o[2] - a[2];
+                        const double u = (sx * hx + sy * hy) * inv;
+                        if (u < 0.0 || u > 1.0) continue;
+                        const double q0 = sy * e1z - sz * e1y, q1 = sz * e1x - sx * e1z, q2 = sx * e1y - sy * e1x;
+                        const double w = q2 * inv;
+                        if (w < 0.0 || u + w > 1.0) continue;
+                        if (inv * (q0 * e2x + q1 * e2y + q2 * e2z) > 0.0) ++hits;
+                    }
+                    if (hits & 1) {
+                        mc.push_back(o[0]);
+                        mc.push_back(o[1]);
+                        mc.push_back(o[2]);
+                        mc.push_back(0.0);
+                    }
+                }
+        cudaFree(ctx->d_mascons);
+        ctx->d_mascons = nullptr;
+        ctx->n_mascons = (int)(mc.size() / 4);
+        if (ctx->n_mascons > 0) {
+            for (int m = 0; m < ctx->n_mascons; ++m) mc[4 * m + 3] = ctx->GM / ctx->n_mascons;
+            const double cell = ((hi[0] - lo[0]) + (hi[1] - lo[1]) + (hi[2] - lo[2])) / (3.0 * G);
+            ctx->mascon_soft2 = 0.25 * cell * cell;
+            TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_mascons, mc.size() * 8));
+            TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_mascons, mc.data(), mc.size() * 8, cudaMemcpyHostToDevice));
+        }
     }
     ctx->Fpad32 = (F + 31) / 32 * 32;
     ctx->n_aos_tiles = (F + kAosTileFaces - 1) / kAosTileFaces;

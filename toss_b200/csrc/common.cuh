@@ -37,7 +37,10 @@ struct toss_ctx {
     int n_aos_tiles = 0;   // ceil(F / 64)
     int n_soa_tiles = 0;   // ceil(F / 128)
     double Grho = 0.0;
-    double GM = 0.0, com[3] = {0.0, 0.0, 0.0};   // G rho V and the centre of mass (work-queue cost predictor)
+    double GM = 0.0, com[3] = {0.0, 0.0, 0.0};   // G rho V and the centre of mass
+    double *d_mascons = nullptr;                 // [n_mascons][4] x y z G*m: proxy field of the work-queue cost predictor
+    int n_mascons = 0;
+    double mascon_soft2 = 0.0;
     double *d_face_aos = nullptr;    // [n_aos_tiles*64][26]
     double *d_face_soa = nullptr;    // [25][Fpad32]
     double *d_face_tiles = nullptr;  // [n_soa_tiles][25][128]

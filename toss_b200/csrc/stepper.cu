@@ -653,26 +653,52 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 
 
 // ------------------------------------------------------------------------------------------------
-// Work-queue ordering.  Trajectory lengths spread 4x (1.3 k .. 5 k RHS evaluations) and there are only ~1.7
-// trajectories per resident warp, so the order in which warps pull them decides the tail.  One thread per
-// trajectory pre-integrates the same chromosome around a softened POINT MASS (G rho V at the centre of mass) with
-// the same RK8(7)-13M controller at rtol = atol = 1e-9; its RHS count is the sort key (descending).  The order
-// only schedules: results are written by trajectory index and do not depend on it.
+// Work-queue ordering (experimental, TOSS_B200_LPT=1).  Trajectory lengths spread 4x (1.3 k .. 5 k RHS evaluations)
+// and a small population has only ~1.7 trajectories per resident warp, so the order in which warps pull them decides
+// the tail.  One thread per trajectory pre-integrates the same chromosome through a MASCON proxy of the body (softened
+// point masses on the cells of an 8^3 grid that lie inside the mesh, rotated like the real field) with the same
+// RK8(7)-13M controller and tolerances; its RHS count is the sort key (descending).  The order only schedules:
+// results are written by trajectory index and do not depend on it.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPredMaxMan = 16;
-constexpr double kPredTol = 1e-9, kPredSoft2 = 1.0e6;   // 1 km softening: the proxy must survive a pass through the body
+constexpr double kPredTolScale = 1.0;   // the proxy integrates at the real tolerances
 
-__device__ __forceinline__ void pm_rhs(const double *y, double GM, double cx, double cy, double cz, double *f)
+// proxy field: a few hundred softened point masses filling the body (toss_ctx::d_mascons), evaluated -- like the real
+// RHS -- at the position rotated by -w t and not rotated back, so the step size sees the same rotating field
+struct PredField {
+    const double *mascons;   // [n][4]: x y z G*m
+    int n;
+    double soft2;
+    UnitAxis axis;
+    double w;
+    int rotate;
+};
+__device__ __forceinline__ void pm_rhs(double t, const double *y, const PredField &F, double *f)
 {
-    const double x = y[0] - cx, yy = y[1] - cy, z = y[2] - cz;
-    const double r2 = x * x + yy * yy + z * z + kPredSoft2;
-    const double g = -GM / (r2 * sqrt(r2));
+    double px = y[0], py = y[1], pz = y[2];
+    if (F.rotate) {
+        double s, c;
+        sincos(-(F.w * t), &s, &c);
+        const double kx = F.axis.x, ky = F.axis.y, kz = F.axis.z;
+        const double cxp = ky * pz - kz * py, cyp = kz * px - kx * pz, czp = kx * py - ky * px;
+        const double kd = (kx * px + ky * py + kz * pz) * (1.0 - c);
+        const double rx = px * c + cxp * s + kx * kd, ry = py * c + cyp * s + ky * kd, rz = pz * c + czp * s + kz * kd;
+        px = rx; py = ry; pz = rz;
+    }
+    double ax = 0.0, ay = 0.0, az = 0.0;
+    for (int k = 0; k < F.n; ++k) {
+        const double dx = px - __ldg(F.mascons + 4 * k), dy = py - __ldg(F.mascons + 4 * k + 1),
+                     dz = pz - __ldg(F.mascons + 4 * k + 2);
+        const double r2 = dx * dx + dy * dy + dz * dz + F.soft2;
+        const double g = __ldg(F.mascons + 4 * k + 3) * rsqrt(r2) / r2;
+        ax -= g * dx; ay -= g * dy; az -= g * dz;
+    }
     f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
-    f[3] = g * x; f[4] = g * yy; f[5] = g * z;
+    f[3] = ax; f[4] = ay; f[5] = az;
 }
 
-__global__ void __launch_bounds__(128) cost_predict_kernel(const StepArgs a, double GM, double cx, double cy,
-                                                           double cz, int32_t *__restrict__ cost)
+__global__ void __launch_bounds__(32) cost_predict_kernel(const StepArgs a, const PredField F,
+                                                           int32_t *__restrict__ cost)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.pop) return;
@@ -706,7 +732,7 @@ __global__ void __launch_bounds__(128) cost_predict_kernel(const StepArgs a, dou
             y[3] = mag * X(9 + 5 * m); y[4] = mag * X(10 + 5 * m); y[5] = mag * X(11 + 5 * m);
         }
         double dt = a.p.initial_time_step;
-        pm_rhs(y, GM, cx, cy, cz, k[0]);
+        pm_rhs(t, y, F, k[0]);
         ++n_rhs;
         while (t < tf && n_rhs < 60000) {
             bool clipped = false;
@@ -721,7 +747,7 @@ __global__ void __launch_bounds__(128) cost_predict_kernel(const StepArgs a, dou
                     for (int j = 0; j < st; ++j) acc = fma(TOSS_RK_A[13 * st + j], k[j][c], acc);
                     ys[c] = fma(dt, acc, y[c]);
                 }
-                pm_rhs(ys, GM, cx, cy, cz, k[st]);
+                pm_rhs(t + TOSS_RK_C[st] * dt, ys, F, k[st]);
             }
             n_rhs += 12;
             double err = 0.0, tol = 0.0, dy[6];
@@ -733,7 +759,7 @@ __global__ void __launch_bounds__(128) cost_predict_kernel(const StepArgs a, dou
                 }
                 dy[c] = dt * s8;
                 err = fmax(err, fabs(dt * se));
-                tol = fmax(tol, kPredTol + kPredTol * fabs(y[c]) + kPredTol * fabs(s8));
+                tol = fmax(tol, kPredTolScale * (a.p.atol + a.p.rtol * fabs(y[c]) + a.p.rtol * fabs(s8)));
             }
             if (!(err == err)) break;
             const double corr = err != 0.0 ? 0.8 * sqrt(sqrt(sqrt(tol / err))) : 1.0;
@@ -746,7 +772,7 @@ __global__ void __launch_bounds__(128) cost_predict_kernel(const StepArgs a, dou
             t = clipped ? tf : t + dt;
             for (int c = 0; c < 6; ++c) y[c] += dy[c];
             dt = newdt;
-            pm_rhs(y, GM, cx, cy, cz, k[0]);
+            pm_rhs(t, y, F, k[0]);
             ++n_rhs;
         }
         t = tf;
@@ -834,10 +860,20 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     // longest-processing-time-first: with ~1.7 trajectories per warp slot and a 4x spread of trajectory lengths the
     // tail of an index-ordered queue costs ~40 %; a cheap point-mass pre-integration predicts the step counts.
     a.order = nullptr;
-    static const bool lpt = getenv("TOSS_B200_LPT") != nullptr;   // experimental: the point-mass proxy predicts poorly (r = 0.25)
-    if (lpt && n_man <= kPredMaxMan && pop > kK2Warps) {
+    // EXPERIMENTAL, off by default: the mascon proxy predicts the RHS counts well (r = 0.96, most of them exactly), but
+    // this one-thread-per-trajectory predictor costs ~180 ms at pop 4096 -- more than the tail it removes; it needs
+    // the warp-per-trajectory treatment (a proxy instantiation of the stepper) before it pays.
+    static const bool lpt = getenv("TOSS_B200_LPT") != nullptr;
+    if (lpt && n_man <= kPredMaxMan && pop > kK2Warps && ctx->n_mascons > 0) {
         int32_t *order = a.queue + 4, *cost = order + pop;
-        cost_predict_kernel<<<(pop + 127) / 128, 128, 0, st>>>(a, ctx->GM, ctx->com[0], ctx->com[1], ctx->com[2], cost);
+        PredField F;
+        F.mascons = ctx->d_mascons;
+        F.n = ctx->n_mascons;
+        F.soft2 = ctx->mascon_soft2;
+        F.axis = a.axis;
+        F.w = p->spin_velocity;
+        F.rotate = p->activate_rotation;
+        cost_predict_kernel<<<(pop + 31) / 32, 32, 0, st>>>(a, F, cost);
         cost_sort_kernel<<<1, 1024, 0, st>>>(cost, pop, order);
         ctx->launches += 2;
         a.order = order;
