@@ -58,6 +58,9 @@ struct StepArgs {
     double *knots_t, *knots_y, *knots_f, *intervals;
     int32_t *seg_start, *n_seg, *collision, *queue;
     const int32_t *order;      // queue position -> trajectory index (longest predicted first), or NULL
+    int proxy_n;               // PROXY instantiation: number of mascons (face_soa then points at [n][4] x y z G*m)
+    double proxy_soft2;
+    int32_t *proxy_cost;       // PROXY: predicted RHS count per trajectory
     toss_counters *counters;
 };
 
@@ -97,13 +100,15 @@ __device__ __forceinline__ void team_bar(int team, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(nthreads) : "memory");
 }
 
-template <bool kStream, int kTeam>
+// kProxy: the same state machine integrating through a mascon proxy of the body (no mesh, no knots, no events); its
+// RHS count per trajectory is the cost key of the longest-first work queue of the real run.
+template <bool kStream, int kTeam, bool kProxy = false>
 __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const StepArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int team = wid / kTeam, rank = wid % kTeam;
-    const int mesh_doubles = kStream ? kK2Stages * kSoaTileDoubles : kFaceFields * a.Fpad32;
+    const int mesh_doubles = kProxy ? 4 * a.proxy_n : (kStream ? kK2Stages * kSoaTileDoubles : kFaceFields * a.Fpad32);
     double *mesh = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(mesh + mesh_doubles);   // full[3] empty[3] (STREAM) / full[1]
     double *wstate = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)wid * warp_state_doubles(a.n_man);
@@ -386,7 +391,16 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 
         // ------------------------------------------------ gravity sweep over all faces
         double ax = 0.0, ay = 0.0, az = 0.0, pv = 0.0;
-        if (kStream) {
+        if (kProxy) {
+            for (int m = lane; m < a.proxy_n; m += 32) {
+                const double dx = Px - mesh[4 * m], dy = Py - mesh[4 * m + 1], dz = Pz - mesh[4 * m + 2];
+                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx)) + a.proxy_soft2;
+                const double g = tm_div(mesh[4 * m + 3], r2 * tm_sqrt(r2));
+                ax = fma(-g, dx, ax);
+                ay = fma(-g, dy, ay);
+                az = fma(-g, dz, az);
+            }
+        } else if (kStream) {
             for (int tl = 0; tl < a.n_tiles; ++tl, ++tile_it) {
                 const int s = tile_it % kK2Stages;
                 // rows of 32 faces in this tile that hold real faces (the last tile is only partly filled)
@@ -497,14 +511,16 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         // k_stage = [ys[3..5], -g_pkg]   (equations_of_motion.py:59,92-95)
         double kc = 0.0;
         if (lane < 3) kc = vsh;
-        else if (lane == 3) kc = -(a.Grho * ax);
-        else if (lane == 4) kc = -(a.Grho * ay);
-        else if (lane == 5) kc = -(a.Grho * az);
+        else if (lane == 3) kc = kProxy ? ax : -(a.Grho * ax);
+        else if (lane == 4) kc = kProxy ? ay : -(a.Grho * ay);
+        else if (lane == 5) kc = kProxy ? az : -(a.Grho * az);
         if (lane < 6) sk[6 * stage + lane] = kc;
         __syncwarp();
         if (stage == 0) {
             // f0 at a segment start or at a freshly accepted state: this is a knot
-            if (nk >= a.knot_cap) {
+            if (kProxy) {
+                // no knots for the proxy run
+            } else if (nk >= a.knot_cap) {
                 status = 3;
             } else {
                 const size_t kb = (size_t)traj * a.knot_cap + nk;
@@ -515,7 +531,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 }
                 ++nk;
             }
-            if (status == 0 && after_accept && p.activate_event &&
+            if (!kProxy && status == 0 && after_accept && p.activate_event &&
                 add_(add_(mul_(qx, qx), mul_(qy, qy)), mul_(qz, qz)) <= R2) {
                 ray_sweep = 1;   // event point: next sweep is its ray cast, then the logic below resumes
                 continue;
@@ -615,7 +631,9 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         }
         // ------------------------------------------------ retire (finished or failed)
         active = false;
-        if (lane == 0) {
+        if (kProxy) {
+            if (lane == 0) a.proxy_cost[traj] = (int32_t)(n_rhs > 2000000000LL ? 2000000000LL : n_rhs);
+        } else if (lane == 0) {
             a.seg_start[(size_t)traj * (a.n_man + 2) + (seg < nseg ? seg + 1 : nseg)] = nk;
             if (status != 0 || stopped) a.n_seg[traj] = seg < nseg ? seg + 1 : nseg;
             toss_counters c;
@@ -653,133 +671,13 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 
 
 // ------------------------------------------------------------------------------------------------
-// Work-queue ordering (experimental, TOSS_B200_LPT=1).  Trajectory lengths spread 4x (1.3 k .. 5 k RHS evaluations)
-// and a small population has only ~1.7 trajectories per resident warp, so the order in which warps pull them decides
-// the tail.  One thread per trajectory pre-integrates the same chromosome through a MASCON proxy of the body (softened
-// point masses on the cells of an 8^3 grid that lie inside the mesh, rotated like the real field) with the same
-// RK8(7)-13M controller and tolerances; its RHS count is the sort key (descending).  The order only schedules:
-// results are written by trajectory index and do not depend on it.
+// Work-queue ordering.  Trajectory lengths spread 4x (1.3 k .. 5 k RHS evaluations) and a small population has only a
+// few trajectories per resident warp, so the order in which warps pull them decides the tail.  The PROXY instantiation
+// of the stepper pre-integrates every chromosome through a mascon model of the body (softened point masses on the
+// cells of an 8^3 grid that lie inside the mesh, rotated like the real field; same controller, same tolerances: its RHS
+// count equals the real one for most trajectories, r = 0.96 overall) at ~5 % of the real cost; the counts are the sort
+// key (longest first).  The order only schedules: results are written by trajectory index and do not depend on it.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPredMaxMan = 16;
-constexpr double kPredTolScale = 1.0;   // the proxy integrates at the real tolerances
-
-// proxy field: a few hundred softened point masses filling the body (toss_ctx::d_mascons), evaluated -- like the real
-// RHS -- at the position rotated by -w t and not rotated back, so the step size sees the same rotating field
-struct PredField {
-    const double *mascons;   // [n][4]: x y z G*m
-    int n;
-    double soft2;
-    UnitAxis axis;
-    double w;
-    int rotate;
-};
-__device__ __forceinline__ void pm_rhs(double t, const double *y, const PredField &F, double *f)
-{
-    double px = y[0], py = y[1], pz = y[2];
-    if (F.rotate) {
-        double s, c;
-        sincos(-(F.w * t), &s, &c);
-        const double kx = F.axis.x, ky = F.axis.y, kz = F.axis.z;
-        const double cxp = ky * pz - kz * py, cyp = kz * px - kx * pz, czp = kx * py - ky * px;
-        const double kd = (kx * px + ky * py + kz * pz) * (1.0 - c);
-        const double rx = px * c + cxp * s + kx * kd, ry = py * c + cyp * s + ky * kd, rz = pz * c + czp * s + kz * kd;
-        px = rx; py = ry; pz = rz;
-    }
-    double ax = 0.0, ay = 0.0, az = 0.0;
-    for (int k = 0; k < F.n; ++k) {
-        const double dx = px - __ldg(F.mascons + 4 * k), dy = py - __ldg(F.mascons + 4 * k + 1),
-                     dz = pz - __ldg(F.mascons + 4 * k + 2);
-        const double r2 = dx * dx + dy * dy + dz * dz + F.soft2;
-        const double g = __ldg(F.mascons + 4 * k + 3) * rsqrt(r2) / r2;
-        ax -= g * dx; ay -= g * dy; az -= g * dz;
-    }
-    f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
-    f[3] = ax; f[4] = ay; f[5] = az;
-}
-
-__global__ void __launch_bounds__(32) cost_predict_kernel(const StepArgs a, const PredField F,
-                                                           int32_t *__restrict__ cost)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.pop) return;
-    auto X = [&](int k) -> double { return k < a.n_fixed ? a.fixed[k] : a.x[(size_t)i * a.dim + (k - a.n_fixed)]; };
-    double y[6] = {X(0), X(1), X(2), X(3) * X(4), X(3) * X(5), X(3) * X(6)};
-    double tm[kPredMaxMan + 2];
-    int idx[kPredMaxMan];
-    const int M = a.n_man;
-    for (int k = 0; k < M; ++k) {
-        tm[k + 1] = (double)(int32_t)X(7 + 5 * k);
-        idx[k] = k;
-    }
-    for (int p = 1; p < M; ++p) {   // insertion sort by time
-        const int v = idx[p];
-        int j = p;
-        while (j > 0 && tm[idx[j - 1] + 1] > tm[v + 1]) {
-            idx[j] = idx[j - 1];
-            --j;
-        }
-        idx[j] = v;
-    }
-    const double t_end = (double)(int32_t)a.p.final_time;
-    double t = (double)(int32_t)a.p.start_time;
-    int n_rhs = 0;
-    double k[13][6];
-    for (int s = 0; s <= M && n_rhs < 60000; ++s) {
-        const double tf = s < M ? tm[idx[s] + 1] : t_end;
-        if (s > 0) {
-            const int m = idx[s - 1];
-            const double mag = X(8 + 5 * m);
-            y[3] = mag * X(9 + 5 * m); y[4] = mag * X(10 + 5 * m); y[5] = mag * X(11 + 5 * m);
-        }
-        double dt = a.p.initial_time_step;
-        pm_rhs(t, y, F, k[0]);
-        ++n_rhs;
-        while (t < tf && n_rhs < 60000) {
-            bool clipped = false;
-            if (t + dt > tf) {
-                dt = tf - t;
-                clipped = true;
-            }
-            for (int st = 1; st < 13; ++st) {
-                double ys[6];
-                for (int c = 0; c < 6; ++c) {
-                    double acc = 0.0;
-                    for (int j = 0; j < st; ++j) acc = fma(TOSS_RK_A[13 * st + j], k[j][c], acc);
-                    ys[c] = fma(dt, acc, y[c]);
-                }
-                pm_rhs(t + TOSS_RK_C[st] * dt, ys, F, k[st]);
-            }
-            n_rhs += 12;
-            double err = 0.0, tol = 0.0, dy[6];
-            for (int c = 0; c < 6; ++c) {
-                double s8 = 0.0, se = 0.0;
-                for (int j = 0; j < 13; ++j) {
-                    s8 = fma(TOSS_RK_B8[j], k[j][c], s8);
-                    se = fma(TOSS_RK_E[j], k[j][c], se);
-                }
-                dy[c] = dt * s8;
-                err = fmax(err, fabs(dt * se));
-                tol = fmax(tol, kPredTolScale * (a.p.atol + a.p.rtol * fabs(y[c]) + a.p.rtol * fabs(s8)));
-            }
-            if (!(err == err)) break;
-            const double corr = err != 0.0 ? 0.8 * sqrt(sqrt(sqrt(tol / err))) : 1.0;
-            const double newdt = corr * dt;
-            if (err > tol) {
-                dt = newdt;
-                if (!(dt > 0.0)) break;
-                continue;
-            }
-            t = clipped ? tf : t + dt;
-            for (int c = 0; c < 6; ++c) y[c] += dy[c];
-            dt = newdt;
-            pm_rhs(t, y, F, k[0]);
-            ++n_rhs;
-        }
-        t = tf;
-    }
-    cost[i] = n_rhs;
-}
-
 // one block: counting sort of the predicted costs, longest first (order within a bin is irrelevant)
 __global__ void __launch_bounds__(1024) cost_sort_kernel(const int32_t *__restrict__ cost, int pop,
                                                          int32_t *__restrict__ order)
@@ -857,34 +755,40 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     a.queue = reinterpret_cast<int32_t *>(ws + L.queue);
     a.counters = reinterpret_cast<toss_counters *>(ws + L.counters);
     TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
-    // longest-processing-time-first: with ~1.7 trajectories per warp slot and a 4x spread of trajectory lengths the
-    // tail of an index-ordered queue costs ~40 %; a cheap point-mass pre-integration predicts the step counts.
-    a.order = nullptr;
-    // EXPERIMENTAL, off by default: the mascon proxy predicts the RHS counts well (r = 0.96, most of them exactly), but
-    // this one-thread-per-trajectory predictor costs ~180 ms at pop 4096 -- more than the tail it removes; it needs
-    // the warp-per-trajectory treatment (a proxy instantiation of the stepper) before it pays.
-    static const bool lpt = getenv("TOSS_B200_LPT") != nullptr;
-    if (lpt && n_man <= kPredMaxMan && pop > kK2Warps && ctx->n_mascons > 0) {
-        int32_t *order = a.queue + 4, *cost = order + pop;
-        PredField F;
-        F.mascons = ctx->d_mascons;
-        F.n = ctx->n_mascons;
-        F.soft2 = ctx->mascon_soft2;
-        F.axis = a.axis;
-        F.w = p->spin_velocity;
-        F.rotate = p->activate_rotation;
-        cost_predict_kernel<<<(pop + 31) / 32, 32, 0, st>>>(a, F, cost);
-        cost_sort_kernel<<<1, 1024, 0, st>>>(cost, pop, order);
-        ctx->launches += 2;
-        a.order = order;
-    }
-
     // warps per trajectory: one when the population fills the machine several times over; two or four below that,
     // which shortens the tail (trajectory lengths spread 4x) and fills the SMs of small populations.  Results do
     // not depend on it.
     const int slots = K2_MINBLOCKS * ctx->sm_count * kK2Warps;
     int team = pop >= 6 * slots ? 1 : (2 * pop >= 3 * slots ? 2 : 4);
     if (const char *e = getenv("TOSS_B200_TEAM")) team = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1);   // developer override
+    // longest-first queue order when trajectories queue for warps (otherwise order is irrelevant), the population is
+    // small enough to have a tail, and the mesh is large enough that the proxy run is cheap next to the real one
+    bool lpt = (long long)pop * team > slots && pop < 6 * slots && ctx->F >= 1000 && ctx->n_mascons > 0;
+    if (const char *e = getenv("TOSS_B200_LPT")) lpt = atoi(e) != 0 && ctx->n_mascons > 0;
+    a.order = nullptr;
+    a.proxy_n = 0;
+    a.proxy_soft2 = 0.0;
+    a.proxy_cost = nullptr;
+    if (lpt) {
+        int32_t *order = a.queue + 4, *cost = order + pop;
+        StepArgs px = a;
+        px.face_soa = ctx->d_mascons;
+        px.proxy_n = ctx->n_mascons;
+        px.proxy_soft2 = ctx->mascon_soft2;
+        px.proxy_cost = cost;
+        const size_t psmem = (size_t)4 * ctx->n_mascons * 8 + (size_t)kK2Warps * warp_state_doubles(n_man) * 8 +
+                             kK2BarSlots * 8 + (size_t)kK2Warps * kTeamBufDoubles * 8;
+        int pctas = (pop + kK2Warps - 1) / kK2Warps;
+        if (pctas > K2_MINBLOCKS * ctx->sm_count) pctas = K2_MINBLOCKS * ctx->sm_count;
+        TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)psmem));
+        stepper_kernel<false, 1, true><<<pctas, kK2Threads, psmem, st>>>(px);
+        cost_sort_kernel<<<1, 1024, 0, st>>>(cost, pop, order);
+        TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 16, st));
+        ctx->launches += 2;
+        a.order = order;
+    }
+
     const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 +
                                (size_t)kK2Warps * kTeamBufDoubles * 8;
     const size_t resident_bytes = (size_t)kFaceFields * ctx->Fpad32 * 8 + state_bytes;
