@@ -85,9 +85,18 @@ int toss_ctx_destroy(toss_ctx *ctx);
 /* Replaces polyhedral_gravity.GravityEvaluable((vertices, faces), density)
  * (toss/optimization/setup_parameters.py:63) and the vertices/faces the ray caster reads
  * (toss/mesh/mesh_utility.py:70-89).  HOST arrays: verts V x 3 (metres), faces F x 3 (CCW outward).
- * Precomputes the per-face constants (normal, edge normals, edge lengths, 2*area) on the device. */
+ * Matches the faces into pairs that share an edge (the unit of the gravity sum: 4 vertex distances and 5 edge
+ * terms per pair instead of 6 and 6) and precomputes the per-pair constants (normals, edge normals, edge
+ * lengths, 2*area) -- what GravityEvaluable precomputes at construction (setup_parameters.py:63). */
 int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t *h_faces, int F, double density);
 int toss_mesh_num_faces(const toss_ctx *ctx);
+/* The pairing: n = toss_mesh_num_pairs records (fA, qA, fB) ascending in fA; A's edge slot qA (v_qA -> v_qA+1)
+ * is the shared edge; fB = -1 for a face left without a partner.  out = int32[3 * n].
+ * toss_pair_faces is the matching alone (host integer work, needs no device or context): out = int32[3 * F]
+ * capacity, returns the number of records or -1. */
+int toss_mesh_num_pairs(const toss_ctx *ctx);
+int toss_mesh_pairs(const toss_ctx *ctx, int32_t *out);
+int toss_pair_faces(const int32_t *h_faces, int F, int V, int32_t *out);
 
 /* Replaces args.problem.tensor_grid_r/theta/phi + bool_tensor
  * (toss/fitness/fitness_function_utils.py:231-279).  HOST arrays; bool_tensor is nr*nth*nph bytes. */
@@ -180,7 +189,7 @@ int toss_measure_fp64_peak(toss_ctx *ctx, double *tflops_out);
 
 /* Test hooks of the arithmetic specification (toss_b200/csrc/tmath.cuh): evaluates elementary function `fn`
  * (0 two_atanh, 1 log, 2 atan2(a,b), 3 sincos -> (out,out2), 4 x^(1/8), 5 x^(1/4), 6 8-term atan series,
- * 7 a/b, 8 sqrt) over n device values; and counts, over `samples` pseudo-random operands, how often the
+ * 7 a/b, 8 sqrt, 9 2 atanh minimax polynomial, 10 2 atan minimax polynomial) over n device values; and counts, over `samples` pseudo-random operands, how often the
  * guard-free division / square root differ from the IEEE-rounded intrinsics (must be 0). */
 int toss_math_probe(toss_ctx *ctx, int fn, const double *d_a, const double *d_b, int64_t n, double *d_out,
                     double *d_out2, uintptr_t stream);

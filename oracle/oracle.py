@@ -80,6 +80,8 @@ def lib():
         L.orc_mesh_create.restype = C.c_void_p
         L.orc_mesh_create.argtypes = [c_double_p, C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_double]
         L.orc_mesh_free.argtypes = [C.c_void_p]
+        L.orc_mesh_pairs.restype = C.c_int
+        L.orc_mesh_pairs.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         L.orc_gravity.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, C.c_int]
         L.orc_gravity_direct.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p]
         L.orc_math_probe.argtypes = [C.c_int, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p]
@@ -205,6 +207,12 @@ class Mesh:
     def n_faces(self):
         return len(self.faces)
 
+    def pairs(self):
+        """The face pairing of the gravity sum: int32 [n][3] rows (fA, qA, fB), fB = -1 for a face left single."""
+        out = np.empty((len(self.faces), 3), np.int32)
+        n = lib().orc_mesh_pairs(self.handle, out.ctypes.data_as(C.POINTER(C.c_int32)))
+        return out[:n].copy()
+
 
 def gravity(mesh: Mesh, pts, threads=1, potential=False):
     """Package-convention acceleration (TOSS uses the negative)."""
@@ -223,7 +231,8 @@ def gravity_direct(mesh: Mesh, pts):
     return acc
 
 
-MATH_FN = dict(two_atanh=0, log=1, atan2=2, sincos=3, root8=4, root4=5, atan_series8=6, div=7, sqrt=8)
+MATH_FN = dict(two_atanh=0, log=1, atan2=2, sincos=3, root8=4, root4=5, atan_series8=6, div=7, sqrt=8,
+               two_atanh_mm=9, two_atan_mm=10)
 
 
 def math_probe(fn: str, a, b=None):

@@ -14,12 +14,16 @@
 
 #define ORC_G 6.67430e-11 /* CODATA-2018, the value polyhedral_gravity >= 2.x uses */
 #define REC 34            /* doubles per face record */
+#define PREC 43           /* doubles per pair record */
 
 struct orc_mesh {
     int V, F;
     double *verts;
     int32_t *faces;
     double *rec; /* per face: v0 v1 v2 | N | g0 g1 g2 | n0 n1 n2 | len0 len1 len2 | 2*area */
+    int n_pairs;
+    int32_t *pairs; /* [n_pairs][3]: fA, qA (A's slot of the shared edge), fB (-1: no partner) */
+    double *prec;   /* per pair: v0 v1 v2 v3 | N_A N_B | nA0 nA1 nA2 | nB0 nB1 nB2 | G0..G4 | 2A_A 2A_B */
     double Grho;
 };
 
@@ -68,6 +72,157 @@ static void parallel_for(int64_t n, int64_t chunk, int threads, pf_body body, vo
     for (int t = 0; t < started; ++t) pthread_join(th[t], NULL);
 }
 
+/* ---------------------------------------------------------------------------------------
+ * Face pairs.  The polyhedral sum is evaluated two faces at a time: faces that share an edge share two
+ * vertices (their distances to the field point) and one edge term LN.  Which faces go together is fixed by a
+ * deterministic matching on the dual graph (Karp-Sipser: faces with a single free neighbour first, FIFO;
+ * otherwise the lowest-numbered free face takes its free neighbour of smallest (degree, edge slot)); records
+ * ascend in the lower face index.  Integer work: any implementation of this rule produces the same list. */
+static int cmp_i64_pair(const void *a, const void *b)
+{
+    const int64_t *x = (const int64_t *)a, *y = (const int64_t *)b;
+    if (x[0] != y[0]) return x[0] < y[0] ? -1 : 1;
+    return x[1] < y[1] ? -1 : (x[1] > y[1] ? 1 : 0);
+}
+static int build_pairs(const int32_t *faces, int F, int V, int32_t *out /* 3*F */)
+{
+    int64_t *he = (int64_t *)malloc(sizeof(int64_t) * 2 * 3 * (size_t)F); /* (key, half-edge id) */
+    for (int h = 0; h < 3 * F; ++h) {
+        const int f = h / 3, q = h % 3;
+        const int64_t u = faces[3 * f + q], v = faces[3 * f + (q + 1) % 3];
+        he[2 * h] = (u < v ? u : v) * (int64_t)V + (u < v ? v : u);
+        he[2 * h + 1] = h;
+    }
+    qsort(he, 3 * (size_t)F, 2 * sizeof(int64_t), cmp_i64_pair);
+    int32_t *nb = (int32_t *)malloc(sizeof(int32_t) * 3 * (size_t)F);
+    for (int h = 0; h < 3 * F; ++h) nb[h] = -1;
+    for (int i = 0; i < 3 * F;) {
+        int j = i;
+        while (j < 3 * F && he[2 * j] == he[2 * i]) ++j;
+        if (j - i == 2) {
+            const int h0 = (int)he[2 * i + 1], h1 = (int)he[2 * i + 3];
+            const int f0 = h0 / 3, q0 = h0 % 3, f1 = h1 / 3, q1 = h1 % 3;
+            if (f0 != f1 && faces[3 * f0 + q0] == faces[3 * f1 + (q1 + 1) % 3] &&
+                faces[3 * f0 + (q0 + 1) % 3] == faces[3 * f1 + q1]) {
+                nb[h0] = f1;
+                nb[h1] = f0;
+            }
+        }
+        i = j;
+    }
+    int32_t *mate = (int32_t *)malloc(sizeof(int32_t) * (size_t)F), *deg = (int32_t *)calloc((size_t)F, sizeof(int32_t));
+    int32_t *fifo = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)F);
+    int head = 0, tail = 0, cur = 0;
+    for (int f = 0; f < F; ++f) {
+        mate[f] = -1;
+        for (int q = 0; q < 3; ++q) deg[f] += nb[3 * f + q] >= 0;
+    }
+    for (int f = 0; f < F; ++f)
+        if (deg[f] == 1) fifo[tail++] = f;
+    for (;;) {
+        int f;
+        if (head < tail) {
+            f = fifo[head++];
+            if (mate[f] >= 0 || deg[f] == 0) continue;
+        } else {
+            while (cur < F && (mate[cur] >= 0 || deg[cur] == 0)) ++cur;
+            if (cur >= F) break;
+            f = cur;
+        }
+        int g = -1;
+        for (int q = 0; q < 3; ++q) {
+            const int h = nb[3 * f + q];
+            if (h >= 0 && mate[h] < 0 && (g < 0 || deg[h] < deg[g])) g = h;
+        }
+        mate[f] = g;
+        mate[g] = f;
+        const int both[2] = {f, g};
+        for (int s = 0; s < 2; ++s)
+            for (int q = 0; q < 3; ++q) {
+                const int h = nb[3 * both[s] + q];
+                if (h >= 0 && mate[h] < 0 && --deg[h] == 1) fifo[tail++] = h;
+            }
+    }
+    int n = 0;
+    for (int f = 0; f < F; ++f) {
+        if (mate[f] < 0) {
+            out[3 * n] = f;
+            out[3 * n + 1] = 0;
+            out[3 * n + 2] = -1;
+            ++n;
+        } else if (f < mate[f]) {
+            int qa = 0;
+            while (nb[3 * f + qa] != mate[f]) ++qa;
+            out[3 * n] = f;
+            out[3 * n + 1] = qa;
+            out[3 * n + 2] = mate[f];
+            ++n;
+        }
+    }
+    free(he);
+    free(nb);
+    free(mate);
+    free(deg);
+    free(fifo);
+    return n;
+}
+
+/* SURVEY.md App. A.1 constants of one face (w0, w1, w2): N = G0 x G1 / |.|, n_q = G_q x N / |.|, |G_q|, 2A */
+static void face_constants(const double *w0, const double *w1, const double *w2, double N[3], double n[9],
+                           double len[3], double *twoA)
+{
+    const double *w[3] = {w0, w1, w2};
+    double Gq[3][3];
+    for (int q = 0; q < 3; ++q)
+        for (int c = 0; c < 3; ++c) Gq[q][c] = w[(q + 1) % 3][c] - w[q][c];
+    cross3(Gq[0], Gq[1], N);
+    const double nn = norm3(N);
+    for (int c = 0; c < 3; ++c) N[c] /= nn;
+    for (int q = 0; q < 3; ++q) {
+        double nq[3];
+        len[q] = norm3(Gq[q]);
+        cross3(Gq[q], N, nq);
+        const double nl = norm3(nq);
+        for (int c = 0; c < 3; ++c) n[3 * q + c] = nq[c] / nl;
+    }
+    *twoA = nn;
+}
+
+/* A = (v0, v1, v2): face fA rotated so that the shared edge comes first; B = (v1, v0, v3): face fB in its own
+ * orientation.  A face without a partner gets a null B (v3 = v2, constants 0). */
+static void pair_record(const double *verts, const int32_t *faces, int fA, int qA, int fB, double *r)
+{
+    const int i0 = faces[3 * fA + qA], i1 = faces[3 * fA + (qA + 1) % 3], i2 = faces[3 * fA + (qA + 2) % 3];
+    int i3 = i2;
+    if (fB >= 0) {
+        int qb = 0;
+        while (!(faces[3 * fB + qb] == i1 && faces[3 * fB + (qb + 1) % 3] == i0)) ++qb;
+        i3 = faces[3 * fB + (qb + 2) % 3];
+    }
+    const double *v0 = verts + 3 * (size_t)i0, *v1 = verts + 3 * (size_t)i1, *v2 = verts + 3 * (size_t)i2,
+                 *v3 = verts + 3 * (size_t)i3;
+    memcpy(r, v0, 24);
+    memcpy(r + 3, v1, 24);
+    memcpy(r + 6, v2, 24);
+    memcpy(r + 9, v3, 24);
+    double len[3], twoA;
+    face_constants(v0, v1, v2, r + 12, r + 18, len, &twoA);
+    r[36] = len[0];
+    r[37] = len[1];
+    r[38] = len[2];
+    r[41] = twoA;
+    if (fB >= 0) {
+        face_constants(v1, v0, v3, r + 15, r + 27, len, &twoA);
+        r[39] = len[1];
+        r[40] = len[2];
+        r[42] = twoA;
+    } else {
+        for (int k = 15; k < 18; ++k) r[k] = 0.0;
+        for (int k = 27; k < 36; ++k) r[k] = 0.0;
+        r[39] = r[40] = r[42] = 0.0;
+    }
+}
+
 /* setup_parameters.py:63  GravityEvaluable((vertices, faces), density): per-face constants
  * of SURVEY.md App. A.1 (segment unit vectors g_q, plane normal N, segment normals n_q). */
 orc_mesh *orc_mesh_create(const double *verts, int V, const int32_t *faces, int F, double density)
@@ -109,6 +264,11 @@ orc_mesh *orc_mesh_create(const double *verts, int V, const int32_t *faces, int 
             r[30 + q] = len;
         }
     }
+    m->pairs = (int32_t *)malloc(sizeof(int32_t) * 3 * (size_t)F);
+    m->n_pairs = build_pairs(faces, F, V, m->pairs);
+    m->prec = (double *)malloc(sizeof(double) * PREC * (size_t)m->n_pairs);
+    for (int i = 0; i < m->n_pairs; ++i)
+        pair_record(verts, faces, m->pairs[3 * i], m->pairs[3 * i + 1], m->pairs[3 * i + 2], m->prec + (size_t)i * PREC);
     return m;
 }
 
@@ -118,10 +278,17 @@ void orc_mesh_free(orc_mesh *m)
     free(m->verts);
     free(m->faces);
     free(m->rec);
+    free(m->pairs);
+    free(m->prec);
     free(m);
 }
 
 int orc_mesh_faces(const orc_mesh *m) { return m->F; }
+int orc_mesh_pairs(const orc_mesh *m, int32_t *out)
+{
+    if (out) memcpy(out, m->pairs, sizeof(int32_t) * 3 * (size_t)m->n_pairs);
+    return m->n_pairs;
+}
 
 /* polyhedral_gravity (Tsoulis 2012) -- SURVEY.md App. A.1, transcribed term by term.  Package sign
  * convention.  Kept as the cross-check of gravity_point() below (orc_gravity_direct). */
@@ -181,68 +348,90 @@ static void gravity_point_direct(const orc_mesh *m, const double P[3], double ac
  * tests/test_oracle_gravity.py which checks both forms against a 50-digit mpmath evaluation.)
  * The direct form loses ~ (l1+l2)/|G| ulps in ln(ratio ~ 1) and in the difference of two O(1)
  * arctangents; this form keeps every term to a few ulp, so it is the one parity is anchored on. */
-/* One face.  Operation order = the arithmetic specification the CUDA kernels implement too
- * (toss_b200/csrc/gravity.cuh face_term): un-fused except where ORC_FMA says so.
- * Fast path (the face is seen under a small solid angle and every edge under a small angle): the four
- * quotients share ONE division, atanh / atan are short odd series.  Otherwise: separate divisions,
+/* One PAIR of faces that share an edge.  Operation order = the arithmetic specification the CUDA kernels
+ * implement too (toss_b200/csrc/gravity.cuh pair_S): un-fused except where ORC_FMA says so.  Shared by the two
+ * faces: |v0 - P|, |v1 - P|, r0.r1, l0*l1 and the edge term LN_0.
+ * Fast path (both faces seen under a small solid angle and every edge under a small angle): the seven
+ * quotients share ONE division, atanh / atan are short odd minimax polynomials.  Otherwise: separate divisions,
  * ln-based atanh, full-range atan2. */
-static inline void face_term(const double *rc, const double P[3], double *ax, double *ay, double *az, double *pv)
+static inline void pair_term(const double *rc, const double P[3], double *ax, double *ay, double *az, double *pv)
 {
     const double r0x = rc[0] - P[0], r0y = rc[1] - P[1], r0z = rc[2] - P[2];
     const double r1x = rc[3] - P[0], r1y = rc[4] - P[1], r1z = rc[5] - P[2];
     const double r2x = rc[6] - P[0], r2y = rc[7] - P[1], r2z = rc[8] - P[2];
+    const double r3x = rc[9] - P[0], r3y = rc[10] - P[1], r3z = rc[11] - P[2];
     const double l0 = sqrt(ORC_FMA(r0z, r0z, ORC_FMA(r0y, r0y, r0x * r0x)));
     const double l1 = sqrt(ORC_FMA(r1z, r1z, ORC_FMA(r1y, r1y, r1x * r1x)));
     const double l2 = sqrt(ORC_FMA(r2z, r2z, ORC_FMA(r2y, r2y, r2x * r2x)));
-    const double *N = rc + 9, *n = rc + 21, *G = rc + 30;
-    const double hp = ORC_FMA(N[2], r0z, ORC_FMA(N[1], r0y, N[0] * r0x));
-    const double hq0 = ORC_FMA(n[2], r0z, ORC_FMA(n[1], r0y, n[0] * r0x));
-    const double hq1 = ORC_FMA(n[5], r1z, ORC_FMA(n[4], r1y, n[3] * r1x));
-    const double hq2 = ORC_FMA(n[8], r2z, ORC_FMA(n[7], r2y, n[6] * r2x));
-    const double A0 = l0 + l1, A1 = l1 + l2, A2 = l2 + l0;
+    const double l3 = sqrt(ORC_FMA(r3z, r3z, ORC_FMA(r3y, r3y, r3x * r3x)));
+    const double *NA = rc + 12, *NB = rc + 15, *nA = rc + 18, *nB = rc + 27, *G = rc + 36;
+    const double hpA = ORC_FMA(NA[2], r0z, ORC_FMA(NA[1], r0y, NA[0] * r0x));
+    const double hpB = ORC_FMA(NB[2], r1z, ORC_FMA(NB[1], r1y, NB[0] * r1x));
+    const double hA0 = ORC_FMA(nA[2], r0z, ORC_FMA(nA[1], r0y, nA[0] * r0x));
+    const double hA1 = ORC_FMA(nA[5], r1z, ORC_FMA(nA[4], r1y, nA[3] * r1x));
+    const double hA2 = ORC_FMA(nA[8], r2z, ORC_FMA(nA[7], r2y, nA[6] * r2x));
+    const double hB0 = ORC_FMA(nB[2], r1z, ORC_FMA(nB[1], r1y, nB[0] * r1x));
+    const double hB1 = ORC_FMA(nB[5], r0z, ORC_FMA(nB[4], r0y, nB[3] * r0x));
+    const double hB2 = ORC_FMA(nB[8], r3z, ORC_FMA(nB[7], r3y, nB[6] * r3x));
+    const double a0 = l0 + l1, a1 = l1 + l2, a2 = l2 + l0, a3 = l0 + l3, a4 = l3 + l1;
+    const double d01 = ORC_FMA(r0z, r1z, ORC_FMA(r0y, r1y, r0x * r1x));
     const double d12 = ORC_FMA(r1z, r2z, ORC_FMA(r1y, r2y, r1x * r2x));
     const double d20 = ORC_FMA(r2z, r0z, ORC_FMA(r2y, r0y, r2x * r0x));
-    const double d01 = ORC_FMA(r0z, r1z, ORC_FMA(r0y, r1y, r0x * r1x));
-    const double den = ORC_FMA(l2, d01, ORC_FMA(l1, d20, ORC_FMA(l0, d12, (l0 * l1) * l2)));
-    const double num = hp * rc[33];
-    double ln0, ln1, ln2, om;
-    int fast = (den > 0.0) && (fabs(num) <= 0.1 * den);
+    const double d03 = ORC_FMA(r0z, r3z, ORC_FMA(r0y, r3y, r0x * r3x));
+    const double d31 = ORC_FMA(r3z, r1z, ORC_FMA(r3y, r1y, r3x * r1x));
+    const double l01 = l0 * l1;
+    const double denA = ORC_FMA(l2, d01, ORC_FMA(l1, d20, ORC_FMA(l0, d12, l01 * l2)));
+    const double denB = ORC_FMA(l3, d01, ORC_FMA(l0, d31, ORC_FMA(l1, d03, l01 * l3)));
+    const double numA = hpA * rc[41], numB = hpB * rc[42];
+    double ln0, ln1, ln2, ln3, ln4, omA, omB;
+    int fast = (denA > 0.0) && (denB > 0.0) && (fabs(numA) <= 0.1 * denA) && (fabs(numB) <= 0.1 * denB);
     if (fast) {
-        const double P01 = A0 * A1, P2D = A2 * den;
-        const double inv = 1.0 / (P01 * P2D);
-        const double i01 = P2D * inv, i2D = P01 * inv;
-        const double z0 = (G[0] * A1) * i01, z1 = (G[1] * A0) * i01, z2 = (G[2] * den) * i2D;
-        const double q = (num * A2) * i2D;
-        const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, qs = q * q;
-        fast = (z0s < 0.04) && (z1s < 0.04) && (z2s < 0.04);
+        const double P01 = a0 * a1, P2A = a2 * denA, P34 = a3 * a4;
+        const double X = P01 * P2A, Y = P34 * denB;
+        const double inv = 1.0 / (X * Y);
+        const double iX = Y * inv, iY = X * inv;
+        const double i01 = P2A * iX, i2A = P01 * iX, i34 = denB * iY, iB = P34 * iY;
+        const double z0 = (G[0] * a1) * i01, z1 = (G[1] * a0) * i01, z2 = (G[2] * denA) * i2A;
+        const double qA = (numA * a2) * i2A;
+        const double z3 = (G[3] * a4) * i34, z4 = (G[4] * a3) * i34;
+        const double qB = numB * iB;
+        const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
+        fast = (z0s < 0.04) && (z1s < 0.04) && (z2s < 0.04) && (z3s < 0.04) && (z4s < 0.04);
         if (fast) {
-            ln0 = orc_two_atanh_series_n(z0, z0s, 11);
-            ln1 = orc_two_atanh_series_n(z1, z1s, 11);
-            ln2 = orc_two_atanh_series_n(z2, z2s, 11);
-            om = 2.0 * orc_atan_series_n(q, qs, 8);
+            ln0 = orc_two_atanh_mm(z0, z0s);
+            ln1 = orc_two_atanh_mm(z1, z1s);
+            ln2 = orc_two_atanh_mm(z2, z2s);
+            ln3 = orc_two_atanh_mm(z3, z3s);
+            ln4 = orc_two_atanh_mm(z4, z4s);
+            omA = orc_two_atan_mm(qA, qA * qA);
+            omB = orc_two_atan_mm(qB, qB * qB);
         }
     }
     if (!fast) {
-        ln0 = orc_two_atanh(G[0] / A0);
-        ln1 = orc_two_atanh(G[1] / A1);
-        ln2 = orc_two_atanh(G[2] / A2);
-        om = 2.0 * orc_atan2(num, den);
+        ln0 = orc_two_atanh(G[0] / a0);
+        ln1 = orc_two_atanh(G[1] / a1);
+        ln2 = orc_two_atanh(G[2] / a2);
+        ln3 = orc_two_atanh(G[3] / a3);
+        ln4 = orc_two_atanh(G[4] / a4);
+        omA = 2.0 * orc_atan2(numA, denA);
+        omB = 2.0 * orc_atan2(numB, denB);
     }
-    const double S = ORC_FMA(-hp, om, ORC_FMA(hq2, ln2, ORC_FMA(hq1, ln1, hq0 * ln0)));
-    *ax = ORC_FMA(N[0], S, *ax);
-    *ay = ORC_FMA(N[1], S, *ay);
-    *az = ORC_FMA(N[2], S, *az);
-    *pv = ORC_FMA(hp, S, *pv);
+    const double SA = ORC_FMA(-hpA, omA, ORC_FMA(hA2, ln2, ORC_FMA(hA1, ln1, hA0 * ln0)));
+    const double SB = ORC_FMA(-hpB, omB, ORC_FMA(hB2, ln4, ORC_FMA(hB1, ln3, hB0 * ln0)));
+    *ax = ORC_FMA(NB[0], SB, ORC_FMA(NA[0], SA, *ax));
+    *ay = ORC_FMA(NB[1], SB, ORC_FMA(NA[1], SA, *ay));
+    *az = ORC_FMA(NB[2], SB, ORC_FMA(NA[2], SA, *az));
+    *pv = ORC_FMA(hpB, SB, ORC_FMA(hpA, SA, *pv));
 }
 
-/* Sum over faces in the order of a 32-lane warp: lane l accumulates faces l, l+32, ... in increasing
+/* Sum over pair records in the order of a 32-lane warp: lane l accumulates records l, l+32, ... in increasing
  * order, then an xor-butterfly adds the 32 partial sums (polyhedral_gravity itself reduces with an
  * unspecified parallel order, so any fixed order is as faithful as another). */
 static void gravity_point(const orc_mesh *m, const double P[3], double acc[3], double *pot)
 {
     double sx[32] = {0.0}, sy[32] = {0.0}, sz[32] = {0.0}, sv[32] = {0.0};
-    for (int f = 0; f < m->F; ++f)
-        face_term(m->rec + (size_t)f * REC, P, &sx[f & 31], &sy[f & 31], &sz[f & 31], &sv[f & 31]);
+    for (int i = 0; i < m->n_pairs; ++i)
+        pair_term(m->prec + (size_t)i * PREC, P, &sx[i & 31], &sy[i & 31], &sz[i & 31], &sv[i & 31]);
     const double ax = orc_butterfly32(sx), ay = orc_butterfly32(sy), az = orc_butterfly32(sz);
     acc[0] = m->Grho * ax;
     acc[1] = m->Grho * ay;
@@ -888,6 +1077,8 @@ void orc_math_probe(int fn, const double *a, const double *b, int64_t n, double 
         case 6: out[i] = orc_atan_series(a[i], 8); break;
         case 7: out[i] = a[i] / b[i]; break;
         case 8: out[i] = sqrt(a[i]); break;
+        case 9: out[i] = orc_two_atanh_mm(a[i], a[i] * a[i]); break;
+        case 10: out[i] = orc_two_atan_mm(a[i], a[i] * a[i]); break;
         default: out[i] = NAN;
         }
     }

@@ -65,6 +65,9 @@ typedef struct {
 orc_mesh *orc_mesh_create(const double *verts, int V, const int32_t *faces, int F, double density);
 void orc_mesh_free(orc_mesh *m);
 int orc_mesh_faces(const orc_mesh *m);
+/* the face pairing the gravity sum runs over: out = int32[n][3] (fA, qA, fB; fB = -1: no partner), or NULL;
+ * returns n.  At most orc_mesh_faces() records. */
+int orc_mesh_pairs(const orc_mesh *m, int32_t *out);
 
 /* polyhedral_gravity.GravityEvaluable.__call__ (call site equations_of_motion.py:58):
  * acc is the PACKAGE sign convention (TOSS negates it, equations_of_motion.py:59). */

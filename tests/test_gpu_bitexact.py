@@ -1,10 +1,11 @@
 """Bit-for-bit parity of the GPU path with the CPU oracle.
 
 Both sides implement ONE arithmetic specification: every value is a fixed sequence of correctly rounded
-IEEE-754 operations (+ - * / sqrt fma rint; oracle/orc_math.h <-> toss_b200/csrc/tmath.cuh), the face sum runs
-in warp order (lane-strided partial sums + xor butterfly) and the sample reductions in 256-thread-block order.
+IEEE-754 operations (+ - * / sqrt fma rint; oracle/orc_math.h <-> toss_b200/csrc/tmath.cuh), the sum over face
+pairs (same deterministic pairing on both sides) runs in warp order (lane-strided partial sums + xor butterfly)
+and the sample reductions in 256-thread-block order.
 So the comparison is `array_equal`, not a tolerance: trajectories, knots, step counts, collision flags,
-voxel counts and fitness values are IDENTICAL.  (The thread-per-point gravity kernel K1a sums the faces
+voxel counts and fitness values are IDENTICAL.  (The thread-per-point gravity kernel K1a sums the pairs
 sequentially instead and agrees to ~1e-14.)"""
 import numpy as np
 import pytest
@@ -33,7 +34,21 @@ def _fn_inputs():
         "atan_series8": (rng.uniform(-0.1, 0.1, n), None),
         "div": (10.0 ** rng.uniform(-20, 20, n) * rng.choice([-1, 1], n), 10.0 ** rng.uniform(-20, 60, n)),
         "sqrt": (10.0 ** rng.uniform(-20, 60, n), None),
+        "two_atanh_mm": (np.concatenate([rng.uniform(-0.2, 0.2, n), 10.0 ** rng.uniform(-9, -1, n)]), None),
+        "two_atan_mm": (np.concatenate([rng.uniform(-0.1, 0.1, n), 10.0 ** rng.uniform(-9, -1, n)]), None),
     }
+
+
+@pytest.mark.parametrize("mesh_name", ["lllp", "llp", "lp", "full"])
+def test_face_pairing_identical(mesh_name):
+    """the library's matching of faces into edge-sharing pairs == the oracle's (integer work, exact)"""
+    c, m = ctx_for(mesh_name)
+    got, ref = c.mesh_pairs(), m.pairs()
+    assert np.array_equal(got, ref)
+    single = ref[:, 2] < 0
+    faces = np.concatenate([ref[:, 0], ref[~single, 2]])
+    assert np.array_equal(np.sort(faces), np.arange(m.n_faces))     # every face exactly once
+    assert single.sum() <= 0.02 * m.n_faces + 2
 
 
 @pytest.mark.parametrize("fn", list(O.MATH_FN))

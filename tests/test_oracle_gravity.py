@@ -90,6 +90,34 @@ def test_gravity_closed_forms_equal_literal_tsoulis(name, n, noise):
     assert rel.max() < noise
 
 
+@pytest.mark.parametrize("name", ["lllp", "llp", "lp", "full"])
+def test_face_pairing(name):
+    """Every face in exactly one record, partners really share the stated edge with opposite directions, almost
+    no face is left single; the library's own (host-only) matching gives the same list."""
+    from toss_b200 import _native as N
+    v, f = O.load_mesh(name)
+    m = O.Mesh(v, f, 533.0)
+    pr = m.pairs()
+    single = pr[:, 2] < 0
+    assert np.array_equal(np.sort(np.concatenate([pr[:, 0], pr[~single, 2]])), np.arange(len(f)))
+    assert np.all(np.diff(pr[:, 0]) > 0) and np.all(pr[~single, 0] < pr[~single, 2])
+    for fa, qa, fb in pr[~single]:
+        a, b = int(f[fa][qa]), int(f[fa][(qa + 1) % 3])
+        assert any(int(f[fb][q]) == b and int(f[fb][(q + 1) % 3]) == a for q in range(3))
+    assert single.sum() <= 0.02 * len(f) + 2
+    assert np.array_equal(N.pair_faces(f, len(v)), pr)
+
+
+def test_pairing_of_an_open_or_inconsistent_surface_degrades_to_singles():
+    """edges with one face, or with two faces running the same way, simply do not pair"""
+    from toss_b200 import _native as N
+    f = np.array([[0, 1, 2], [0, 1, 3], [4, 5, 6]], np.int32)       # 0-1 is traversed the same way twice
+    pr = N.pair_faces(f, 7)
+    assert np.array_equal(pr, [[0, 0, -1], [1, 0, -1], [2, 0, -1]])
+    f = np.array([[0, 1, 2], [1, 0, 3]], np.int32)
+    assert np.array_equal(N.pair_faces(f, 4), [[0, 0, 1]])
+
+
 def test_gravity_far_field_point_mass():
     v, f = O.load_mesh("llp")
     m = O.Mesh(v, f)

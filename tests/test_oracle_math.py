@@ -35,6 +35,19 @@ def test_atan2_all_quadrants_and_small_series():
     assert ulps(O.math_probe("atan_series8", q), np.arctan(q)).max() <= 2
 
 
+def test_minimax_polynomials_of_the_common_path():
+    """2 atanh(z) on z^2 <= 0.04 (7 coefficients) and 2 atan(t) on t^2 <= 0.01 (5): within 2 ulp of libm"""
+    rng = np.random.default_rng(7)
+    z = np.concatenate([rng.uniform(-0.2, 0.2, 300000), 10.0 ** rng.uniform(-9, -1, 50000), [0.2, -0.2, 0.0]])
+    got, ref = O.math_probe("two_atanh_mm", z), 2 * np.arctanh(z)
+    nz = ref != 0
+    assert ulps(got[nz], ref[nz]).max() <= 2 and np.all(got[~nz] == 0)
+    t = np.concatenate([rng.uniform(-0.1, 0.1, 300000), 10.0 ** rng.uniform(-9, -1, 50000), [0.1, -0.1, 0.0]])
+    got, ref = O.math_probe("two_atan_mm", t), 2 * np.arctan(t)
+    nz = ref != 0
+    assert ulps(got[nz], ref[nz]).max() <= 2 and np.all(got[~nz] == 0)
+
+
 def test_sincos():
     rng = np.random.default_rng(2)
     th = np.concatenate([rng.uniform(-100, 100, 400000), rng.uniform(-1e4, 1e4, 100000), [0.0, np.pi / 4, -np.pi / 2]])

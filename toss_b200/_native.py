@@ -55,7 +55,7 @@ COUNTERS_DTYPE = np.dtype(
 
 EXPORTS = [
     "toss_version", "toss_last_error", "toss_ctx_create", "toss_ctx_destroy", "toss_mesh_upload",
-    "toss_mesh_num_faces", "toss_grid_upload", "toss_gravity_eval", "toss_compute_motion",
+    "toss_mesh_num_faces", "toss_mesh_num_pairs", "toss_mesh_pairs", "toss_pair_faces", "toss_grid_upload", "toss_gravity_eval", "toss_compute_motion",
     "toss_rotate_points", "toss_workspace_layout", "toss_propagate", "toss_integrate", "toss_collision_verdict", "toss_num_samples", "toss_resample", "toss_dense_eval",
     "toss_fitness_eval", "toss_update_tensor", "toss_is_outside", "toss_population_fitness",
     "toss_population_fitness_host", "toss_measure_fp64_peak", "toss_launch_count", "toss_math_probe",
@@ -95,6 +95,9 @@ def lib():
     L.toss_ctx_destroy.argtypes = [vp]
     L.toss_mesh_upload.argtypes = [vp, c_double_p, i32, C.POINTER(C.c_int32), i32, dbl]
     L.toss_mesh_num_faces.argtypes = [vp]
+    L.toss_mesh_num_pairs.argtypes = [vp]
+    L.toss_mesh_pairs.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.toss_pair_faces.argtypes = [C.POINTER(C.c_int32), i32, i32, C.POINTER(C.c_int32)]
     L.toss_grid_upload.argtypes = [vp, c_double_p, i32, c_double_p, i32, c_double_p, i32, C.POINTER(C.c_uint8)]
     L.toss_gravity_eval.argtypes = [vp, vp, i64, vp, vp, up]
     L.toss_compute_motion.argtypes = [vp, pp, vp, vp, i64, vp, up]
@@ -172,6 +175,17 @@ def make_params(**kw) -> TossParams:
     return p
 
 
+def pair_faces(faces, n_vertices: int):
+    """toss_pair_faces: the matching of a triangle list into edge-sharing pairs (host integer work, no device)."""
+    f = np.ascontiguousarray(faces, dtype=np.int32)
+    out = np.empty((len(f), 3), np.int32)
+    n = lib().toss_pair_faces(f.ctypes.data_as(C.POINTER(C.c_int32)), len(f), int(n_vertices),
+                              out.ctypes.data_as(C.POINTER(C.c_int32)))
+    if n < 0:
+        raise ValueError("toss_pair_faces: bad triangle list")
+    return out[:n].copy()
+
+
 class Context:
     """One device context (mesh + voxel grid resident in HBM).  Buffers are torch CUDA tensors."""
 
@@ -208,6 +222,13 @@ class Context:
         _check(lib().toss_mesh_upload(self.h, _dp(v), len(v), f.ctypes.data_as(C.POINTER(C.c_int32)), len(f),
                                       float(density)))
         self.n_faces = len(f)
+
+    def mesh_pairs(self):
+        """The face pairing of the gravity sum: int32 [n][3] rows (fA, qA, fB), fB = -1 for a face left single."""
+        n = lib().toss_mesh_num_pairs(self.h)
+        out = np.empty((n, 3), np.int32)
+        _check(lib().toss_mesh_pairs(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
 
     def upload_grid(self, r, theta, phi, bool_tensor):
         r, theta, phi = _f64(r), _f64(theta), _f64(phi)

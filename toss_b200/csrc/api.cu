@@ -36,12 +36,16 @@ int toss_ctx_create(int device, toss_ctx **out)
 
 static void free_mesh(toss_ctx *c)
 {
-    cudaFree(c->d_face_aos);
-    cudaFree(c->d_face_soa);
-    cudaFree(c->d_face_tiles);
+    cudaFree(c->d_pair_aos);
+    cudaFree(c->d_pair_soa);
+    cudaFree(c->d_pair_tiles);
+    cudaFree(c->d_ray_soa);
     cudaFree(c->d_mascons);
-    c->d_face_aos = c->d_face_soa = c->d_face_tiles = c->d_mascons = nullptr;
+    free(c->h_pairs);
+    c->d_pair_aos = c->d_pair_soa = c->d_pair_tiles = c->d_ray_soa = c->d_mascons = nullptr;
+    c->h_pairs = nullptr;
     c->n_mascons = 0;
+    c->n_pairs = 0;
 }
 static void free_grid(toss_ctx *c)
 {
@@ -66,6 +70,24 @@ int toss_ctx_destroy(toss_ctx *ctx)
 }
 
 int toss_mesh_num_faces(const toss_ctx *ctx) { return ctx ? ctx->F : 0; }
+int toss_mesh_num_pairs(const toss_ctx *ctx) { return ctx ? ctx->n_pairs : 0; }
+int toss_mesh_pairs(const toss_ctx *ctx, int32_t *out)
+{
+    TOSS_REQUIRE(ctx && out && ctx->h_pairs, "toss_mesh_pairs: no mesh uploaded");
+    memcpy(out, ctx->h_pairs, sizeof(int32_t) * 3 * (size_t)ctx->n_pairs);
+    return 0;
+}
+// the matching alone (host integer work, no device): out = int32[3 * F] capacity, returns the number of records
+int toss_pair_faces(const int32_t *h_faces, int F, int V, int32_t *out)
+{
+    if (!h_faces || !out || F <= 0 || V <= 0) return -1;
+    for (int i = 0; i < 3 * F; ++i)
+        if (h_faces[i] < 0 || h_faces[i] >= V) return -1;
+    std::vector<int32_t> pairs;
+    toss_build_face_pairs(h_faces, F, V, pairs);
+    memcpy(out, pairs.data(), sizeof(int32_t) * pairs.size());
+    return (int)(pairs.size() / 3);
+}
 int64_t toss_launch_count(const toss_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 // Per-face constants of SURVEY.md App. A.1 (what GravityEvaluable precomputes at construction,
@@ -77,36 +99,18 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
     TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
     for (int i = 0; i < 3 * F; ++i)
         TOSS_REQUIRE(h_faces[i] >= 0 && h_faces[i] < V, "toss_mesh_upload: face index out of range");
-    std::vector<double> rec((size_t)F * kFaceFields);
-    for (int f = 0; f < F; ++f) {
-        double *r = &rec[(size_t)f * kFaceFields];
-        const double *v[3];
-        for (int i = 0; i < 3; ++i) {
-            v[i] = h_verts + 3 * (size_t)h_faces[3 * f + i];
-            for (int c = 0; c < 3; ++c) r[3 * i + c] = v[i][c];
-        }
-        double G[3][3];
-        for (int q = 0; q < 3; ++q)
-            for (int c = 0; c < 3; ++c) G[q][c] = v[(q + 1) % 3][c] - v[q][c];
-        double N[3] = {G[0][1] * G[1][2] - G[0][2] * G[1][1], G[0][2] * G[1][0] - G[0][0] * G[1][2],
-                       G[0][0] * G[1][1] - G[0][1] * G[1][0]};
-        const double nn = sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
-        TOSS_REQUIRE(nn > 0.0, "toss_mesh_upload: degenerate (zero-area) face");
-        for (int c = 0; c < 3; ++c) N[c] /= nn;
-        for (int c = 0; c < 3; ++c) r[9 + c] = N[c];
-        for (int q = 0; q < 3; ++q) {
-            const double len = sqrt(G[q][0] * G[q][0] + G[q][1] * G[q][1] + G[q][2] * G[q][2]);
-            double nq[3] = {G[q][1] * N[2] - G[q][2] * N[1], G[q][2] * N[0] - G[q][0] * N[2],
-                            G[q][0] * N[1] - G[q][1] * N[0]};
-            const double nl = sqrt(nq[0] * nq[0] + nq[1] * nq[1] + nq[2] * nq[2]);
-            for (int c = 0; c < 3; ++c) r[12 + 3 * q + c] = nq[c] / nl;
-            r[21 + q] = len;
-        }
-        r[24] = nn;
-    }
-    auto pad_rec = [](double *r) {
-        for (int k = 0; k < kFaceFields; ++k) r[k] = 0.0;
-        for (int k = 0; k < 9; ++k) r[k] = kPadVertex;
+    // the pairing and the per-pair constants (pairs.cu)
+    std::vector<int32_t> pairs;
+    toss_build_face_pairs(h_faces, F, V, pairs);
+    const int n_pairs = (int)(pairs.size() / 3);
+    std::vector<double> rec((size_t)n_pairs * kPairFields);
+    for (int i = 0; i < n_pairs; ++i)
+        TOSS_REQUIRE(toss_pair_record(h_verts, h_faces, pairs[3 * i], pairs[3 * i + 1], pairs[3 * i + 2],
+                                      &rec[(size_t)i * kPairFields]),
+                     "toss_mesh_upload: degenerate (zero-area) face");
+    auto pair_or_pad = [&](int i, double *out) {
+        if (i < n_pairs) memcpy(out, &rec[(size_t)i * kPairFields], sizeof(double) * kPairFields);
+        else toss_pair_pad_record(out);
     };
     free_mesh(ctx);
     ctx->V = V;
@@ -174,42 +178,45 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
         }
     }
     ctx->Fpad32 = (F + 31) / 32 * 32;
-    ctx->n_aos_tiles = (F + kAosTileFaces - 1) / kAosTileFaces;
-    ctx->n_soa_tiles = (F + kSoaTileFaces - 1) / kSoaTileFaces;
+    ctx->n_pairs = n_pairs;
+    ctx->Ppad32 = (n_pairs + 31) / 32 * 32;
+    ctx->n_pair_aos_tiles = (n_pairs + kPairAosTile - 1) / kPairAosTile;
+    ctx->n_pair_tiles = (n_pairs + kPairTile - 1) / kPairTile;
+    ctx->h_pairs = (int32_t *)malloc(sizeof(int32_t) * pairs.size());
+    memcpy(ctx->h_pairs, pairs.data(), sizeof(int32_t) * pairs.size());
 
-    // (1) AoS, 26 doubles per face, padded to whole 64-face tiles      -> K1 thread-per-point
-    std::vector<double> aos((size_t)ctx->n_aos_tiles * kAosTileFaces * kAosStride, 0.0);
-    for (int f = 0; f < ctx->n_aos_tiles * kAosTileFaces; ++f) {
-        double tmp[kFaceFields];
-        if (f < F) memcpy(tmp, &rec[(size_t)f * kFaceFields], sizeof(tmp));
-        else pad_rec(tmp);
-        memcpy(&aos[(size_t)f * kAosStride], tmp, sizeof(tmp));
+    // (1) AoS, 44 doubles per pair, padded to whole 32-pair tiles          -> K1a thread-per-point
+    std::vector<double> aos((size_t)ctx->n_pair_aos_tiles * kPairAosTile * kPairAosStride, 0.0);
+    for (int i = 0; i < ctx->n_pair_aos_tiles * kPairAosTile; ++i) pair_or_pad(i, &aos[(size_t)i * kPairAosStride]);
+    // (2) flat SoA [43][Ppad32]                                           -> resident stepper, K1b
+    std::vector<double> soa((size_t)kPairFields * ctx->Ppad32);
+    for (int i = 0; i < ctx->Ppad32; ++i) {
+        double tmp[kPairFields];
+        pair_or_pad(i, tmp);
+        for (int k = 0; k < kPairFields; ++k) soa[(size_t)k * ctx->Ppad32 + i] = tmp[k];
     }
-    // (2) flat SoA [25][Fpad32]                                          -> resident stepper, K1b, K5
-    std::vector<double> soa((size_t)kFaceFields * ctx->Fpad32);
-    for (int f = 0; f < ctx->Fpad32; ++f) {
-        double tmp[kFaceFields];
-        if (f < F) memcpy(tmp, &rec[(size_t)f * kFaceFields], sizeof(tmp));
-        else pad_rec(tmp);
-        for (int k = 0; k < kFaceFields; ++k) soa[(size_t)k * ctx->Fpad32 + f] = tmp[k];
-    }
-    // (3) tiled SoA [n_tiles][25][128] -> streaming stepper.  Face f sits in tile f/128, slot f%128, so lane l
-    //     still owns faces l, l+32, l+64, ... in increasing order: the same summation order as the flat layout.
-    std::vector<double> tiles((size_t)ctx->n_soa_tiles * kSoaTileDoubles);
-    for (int t = 0; t < ctx->n_soa_tiles; ++t)
-        for (int j = 0; j < kSoaTileFaces; ++j) {
-            const int f = t * kSoaTileFaces + j;
-            double tmp[kFaceFields];
-            if (f < F) memcpy(tmp, &rec[(size_t)f * kFaceFields], sizeof(tmp));
-            else pad_rec(tmp);
-            for (int k = 0; k < kFaceFields; ++k) tiles[((size_t)t * kFaceFields + k) * kSoaTileFaces + j] = tmp[k];
+    // (3) tiled SoA [n_tiles][43][128] -> streaming stepper.  Pair i sits in tile i/128, slot i%128, so lane l
+    //     still owns pairs l, l+32, l+64, ... in increasing order: the same summation order as the flat layout.
+    std::vector<double> tiles((size_t)ctx->n_pair_tiles * kPairTileDoubles);
+    for (int t = 0; t < ctx->n_pair_tiles; ++t)
+        for (int j = 0; j < kPairTile; ++j) {
+            double tmp[kPairFields];
+            pair_or_pad(t * kPairTile + j, tmp);
+            for (int k = 0; k < kPairFields; ++k) tiles[((size_t)t * kPairFields + k) * kPairTile + j] = tmp[k];
         }
-    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_face_aos, aos.size() * 8));
-    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_face_soa, soa.size() * 8));
-    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_face_tiles, tiles.size() * 8));
-    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_face_aos, aos.data(), aos.size() * 8, cudaMemcpyHostToDevice));
-    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_face_soa, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice));
-    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_face_tiles, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice));
+    // (4) the faces themselves, original vertex order, [9][Fpad32]        -> ray casting (K5, event points)
+    std::vector<double> ray((size_t)kRayFields * ctx->Fpad32);
+    for (int f = 0; f < ctx->Fpad32; ++f)
+        for (int k = 0; k < kRayFields; ++k)
+            ray[(size_t)k * ctx->Fpad32 + f] = f < F ? h_verts[3 * (size_t)h_faces[3 * f + k / 3] + k % 3] : kPadVertex;
+    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_pair_aos, aos.size() * 8));
+    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_pair_soa, soa.size() * 8));
+    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_pair_tiles, tiles.size() * 8));
+    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_ray_soa, ray.size() * 8));
+    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_pair_aos, aos.data(), aos.size() * 8, cudaMemcpyHostToDevice));
+    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_pair_soa, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice));
+    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_pair_tiles, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice));
+    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_ray_soa, ray.data(), ray.size() * 8, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -449,7 +456,7 @@ int toss_math_probe(toss_ctx *ctx, int fn, const double *d_a, const double *d_b,
                     double *d_out2, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && (n == 0 || (d_a && d_out)), "toss_math_probe: NULL argument");
-    TOSS_REQUIRE(fn >= 0 && fn <= 8, "toss_math_probe: unknown function id");
+    TOSS_REQUIRE(fn >= 0 && fn <= 10, "toss_math_probe: unknown function id");
     TOSS_REQUIRE(!(fn == 2 || fn == 7) || d_b, "toss_math_probe: this function needs a second operand");
     TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
     return launch_math_probe(ctx, fn, d_a, d_b, n, d_out, d_out2, (cudaStream_t)stream);

@@ -9,21 +9,29 @@
 #include "tmath.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// face record: 25 doubles per face (SURVEY.md App. A.1 constants that do not depend on the field point)
-//   0..8   v0 v1 v2          vertices (also what the ray caster reads, mesh_utility.py:132-166)
-//   9..11  N                 unit outward plane normal
-//   12..20 n0 n1 n2          unit in-plane outward edge normals
-//   21..23 |G0| |G1| |G2|    edge lengths
-//   24     2*area            |G0 x G1|   (r0.(r1 x r2) = (N.r0) * 2A)
+// pair record: two faces that share an edge, 43 doubles (SURVEY.md App. A.1 constants that do not depend on the
+// field point).  A = (v0, v1, v2), B = (v1, v0, v3), each in the orientation the mesh gives it; edges
+// e0 = v0v1 (shared), e1 = v1v2, e2 = v2v0, e3 = v0v3, e4 = v3v1.
+//   0..11  v0 v1 v2 v3
+//   12..14 N_A      15..17 N_B           unit outward plane normals
+//   18..26 nA0 nA1 nA2                   A's unit in-plane outward edge normals (edges e0 e1 e2)
+//   27..35 nB0 nB1 nB2                   B's (edges e0 e3 e4)
+//   36..40 |G0| .. |G4|                  edge lengths
+//   41 2*area(A)    42 2*area(B)         (r0.(r1 x r2) = (N.r0) * 2A)
+// A face without a partner has a null B (v3 = v2, B's constants 0: S_B = 0 exactly); padding records sit at
+// kPadVertex with every constant 0 and contribute exactly 0.
+// The ray caster (mesh_utility.py:132-166) reads the faces in their ORIGINAL vertex order from a separate
+// [9][Fpad32] table.
 // ------------------------------------------------------------------------------------------------
-constexpr int kFaceFields = 25;
-constexpr int kAosStride = 26;          // AoS record padded to 208 B = 13 x 16 B (LDS.128 broadcast reads)
-constexpr int kAosTileFaces = 64;       // K1 (thread-per-point) TMA tile: 64 x 208 B = 13 312 B
-#ifndef SOA_TILE_FACES
-#define SOA_TILE_FACES 128
+constexpr int kPairFields = 43;
+constexpr int kPairAosStride = 44;      // AoS pair record padded to 352 B = 22 x 16 B (LDS.128 broadcast reads)
+constexpr int kPairAosTile = 32;        // K1 (thread-per-point) TMA tile: 32 pairs x 352 B = 11 264 B
+#ifndef PAIR_TILE
+#define PAIR_TILE 128
 #endif
-constexpr int kSoaTileFaces = SOA_TILE_FACES;   // K2 (lane-per-face) TMA tile: 25 x 128 x 8 B = 25 600 B
-constexpr int kSoaTileDoubles = kFaceFields * kSoaTileFaces;
+constexpr int kPairTile = PAIR_TILE;    // K2 (lane-per-pair) TMA tile: 43 x 128 x 8 B = 44 032 B, 4 rows of 32 pairs
+constexpr int kPairTileDoubles = kPairFields * kPairTile;
+constexpr int kRayFields = 9;
 constexpr double kPadVertex = 1.0e9;    // padding faces sit here with N = n = |G| = 2A = 0 -> contribute exactly 0
 constexpr double kGravConst = 6.67430e-11;   // CODATA-2018, as polyhedral_gravity >= 2
 
@@ -33,17 +41,21 @@ struct toss_ctx {
     int max_smem_optin = 0;
     // mesh
     int V = 0, F = 0;
-    int Fpad32 = 0;        // F rounded up to 32  (flat SoA, resident mode)
-    int n_aos_tiles = 0;   // ceil(F / 64)
-    int n_soa_tiles = 0;   // ceil(F / 128)
+    int Fpad32 = 0;        // F rounded up to 32
     double Grho = 0.0;
     double GM = 0.0, com[3] = {0.0, 0.0, 0.0};   // G rho V and the centre of mass
     double *d_mascons = nullptr;                 // [n_mascons][4] x y z G*m: proxy field of the work-queue cost predictor
     int n_mascons = 0;
     double mascon_soft2 = 0.0;
-    double *d_face_aos = nullptr;    // [n_aos_tiles*64][26]
-    double *d_face_soa = nullptr;    // [25][Fpad32]
-    double *d_face_tiles = nullptr;  // [n_soa_tiles][25][128]
+    int n_pairs = 0;                 // pair records (matched pairs + faces left single)
+    int Ppad32 = 0;                  // n_pairs rounded up to 32 (flat SoA)
+    int n_pair_aos_tiles = 0;        // ceil(n_pairs / 32)
+    int n_pair_tiles = 0;            // ceil(n_pairs / 128)
+    double *d_pair_aos = nullptr;    // [n_pair_aos_tiles*32][44]      K1a
+    double *d_pair_soa = nullptr;    // [43][Ppad32]                   K1b, resident stepper
+    double *d_pair_tiles = nullptr;  // [n_pair_tiles][43][128]        streaming stepper
+    double *d_ray_soa = nullptr;     // [9][Fpad32] v0 v1 v2 of every face in mesh order: ray casting
+    int32_t *h_pairs = nullptr;      // [n_pairs][3] fA, qA, fB: the pairing (toss_mesh_pairs)
     // voxel grid
     int nr = 0, nth = 0, nph = 0;
     double *d_grid = nullptr;        // r | theta | phi
@@ -127,6 +139,12 @@ inline UnitAxis unit_axis_host(const double a[3])
     double n = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
     return UnitAxis{a[0] / n, a[1] / n, a[2] / n};
 }
+
+// ---- face pairing (pairs.cu) -------------------------------------------------------------------------
+#include <vector>
+void toss_build_face_pairs(const int32_t *faces, int F, int V, std::vector<int32_t> &out);
+bool toss_pair_record(const double *verts, const int32_t *faces, int fA, int qA, int fB, double *rec43);
+void toss_pair_pad_record(double *rec43);
 
 // ---- kernels' host launchers (defined in the .cu files) -------------------------------------------
 int launch_gravity(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc, double *d_pot, cudaStream_t st);

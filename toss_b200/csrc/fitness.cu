@@ -546,7 +546,7 @@ int launch_collision(toss_ctx *ctx, const toss_params *p, void *d_ws, int pop, i
 {
     WsPtrs w = ws_ptrs(d_ws, pop, n_man, knot_cap);
     const int blocks = (pop * 32 + 255) / 256;
-    collision_kernel<<<blocks, 256, 0, st>>>(*p, ctx->d_face_soa, ctx->Fpad32, w.knots_y, w.seg_start, w.n_seg, n_man,
+    collision_kernel<<<blocks, 256, 0, st>>>(*p, ctx->d_ray_soa, ctx->Fpad32, w.knots_y, w.seg_start, w.n_seg, n_man,
                                              knot_cap, pop, w.collision, w.counters);
     ctx->launches++;
     TOSS_CHECK_CUDA(cudaGetLastError());

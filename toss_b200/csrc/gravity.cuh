@@ -1,4 +1,4 @@
-// toss_b200/csrc/gravity.cuh -- the polyhedral-gravity face term and the TMA/mbarrier tile plumbing.
+// toss_b200/csrc/gravity.cuh -- the polyhedral-gravity face-pair term and the TMA/mbarrier tile plumbing.
 //
 // Replaces polyhedral_gravity.GravityEvaluable.__call__ (call site toss/trajectory/equations_of_motion.py:58).
 // Tsoulis (2012) line-integral sum, per face p with edges q:
@@ -9,79 +9,102 @@
 //     LN_pq = ln((s2+l2)/(s1+l1)) = 2 atanh(|G_pq| / (l1 + l2))
 //     hp (sum_q sigma_pq AN_pq + singA_p) = -hp_s * omega_p,
 //     omega_p = 2 atan2(r0.(r1 x r2), l0 l1 l2 + l0 (r1.r2) + l1 (r2.r0) + l2 (r0.r1))
-// Work per face-point pair on the common path (face seen under a small solid angle, edges under small
-// angles): 3 sqrt, ONE division shared by the four quotients, three 11-term atanh series, one 8-term atan
-// series, ~60 other FP64 instructions -- everything on the FP64 pipe, nothing to feed tensor cores.  Faces
-// close to the field point take the general path (separate divisions, ln-based atanh, full-range atan2).
-// Every operation is spelled out (tmath.cuh): the value is a fixed sequence of IEEE operations.
+// The unit of work is a PAIR of faces that share an edge (pairs.cu): LN of an edge depends only on its two end
+// points, |v - P| only on the vertex, so a pair needs 4 square roots and 5 edge terms where two single faces need
+// 6 and 6.  Work per pair-point on the common path (both faces seen under a small solid angle, edges under small
+// angles): 4 sqrt, ONE division shared by the seven quotients, five 7-coefficient atanh polynomials, two
+// 5-coefficient atan polynomials, ~110 other FP64 instructions -- everything on the FP64 pipe, nothing to feed
+// tensor cores.  A pair with a face close to the field point takes the general path (separate divisions, ln-based
+// atanh, full-range atan2).  Every operation is spelled out (tmath.cuh): the value is a fixed sequence of IEEE
+// operations.
 #pragma once
 #include "common.cuh"
 #include "tmath.cuh"
 
-// One face, one field point P.  fld(k) returns field k of the face record (common.cuh layout); the
-// accessor decides where it comes from (shared-memory AoS broadcast, shared-memory SoA, global SoA).
-// S_p of one face (the scalar that multiplies N_p); hp_out = signed plane distance (potential term).
+// Two faces that share an edge, one field point (pair record of common.cuh): S_A and S_B, the scalars that
+// multiply N_A and N_B.  Shared between the two: the distances to v0 and v1, r0.r1, l0*l1 and the edge term
+// LN_0 of e0; on the common path ONE division serves the five edge quotients and the two solid-angle quotients.
 template <class Fld>
-__device__ __forceinline__ double face_S(Fld fld, double Px, double Py, double Pz, double &hp_out)
+__device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz, double &SA, double &SB,
+                                       double &hpA_out, double &hpB_out)
 {
     const double r0x = fld(0) - Px, r0y = fld(1) - Py, r0z = fld(2) - Pz;
     const double r1x = fld(3) - Px, r1y = fld(4) - Py, r1z = fld(5) - Pz;
     const double r2x = fld(6) - Px, r2y = fld(7) - Py, r2z = fld(8) - Pz;
+    const double r3x = fld(9) - Px, r3y = fld(10) - Py, r3z = fld(11) - Pz;
     const double l0 = tm_sqrt(fma(r0z, r0z, fma(r0y, r0y, r0x * r0x)));
     const double l1 = tm_sqrt(fma(r1z, r1z, fma(r1y, r1y, r1x * r1x)));
     const double l2 = tm_sqrt(fma(r2z, r2z, fma(r2y, r2y, r2x * r2x)));
-    const double Nx = fld(9), Ny = fld(10), Nz = fld(11);
-    const double hp = fma(Nz, r0z, fma(Ny, r0y, Nx * r0x));                  // signed plane distance
-    const double hq0 = fma(fld(14), r0z, fma(fld(13), r0y, fld(12) * r0x));  // signed edge-line distances
-    const double hq1 = fma(fld(17), r1z, fma(fld(16), r1y, fld(15) * r1x));
-    const double hq2 = fma(fld(20), r2z, fma(fld(19), r2y, fld(18) * r2x));
-    const double A0 = l0 + l1, A1 = l1 + l2, A2 = l2 + l0;
+    const double l3 = tm_sqrt(fma(r3z, r3z, fma(r3y, r3y, r3x * r3x)));
+    const double hpA = fma(fld(14), r0z, fma(fld(13), r0y, fld(12) * r0x));     // N_A . r0
+    const double hpB = fma(fld(17), r1z, fma(fld(16), r1y, fld(15) * r1x));     // N_B . r1 (B's first vertex)
+    const double hA0 = fma(fld(20), r0z, fma(fld(19), r0y, fld(18) * r0x));     // A: e0 at v0, e1 at v1, e2 at v2
+    const double hA1 = fma(fld(23), r1z, fma(fld(22), r1y, fld(21) * r1x));
+    const double hA2 = fma(fld(26), r2z, fma(fld(25), r2y, fld(24) * r2x));
+    const double hB0 = fma(fld(29), r1z, fma(fld(28), r1y, fld(27) * r1x));     // B: e0 at v1, e3 at v0, e4 at v3
+    const double hB1 = fma(fld(32), r0z, fma(fld(31), r0y, fld(30) * r0x));
+    const double hB2 = fma(fld(35), r3z, fma(fld(34), r3y, fld(33) * r3x));
+    const double a0 = l0 + l1, a1 = l1 + l2, a2 = l2 + l0, a3 = l0 + l3, a4 = l3 + l1;
+    const double d01 = fma(r0z, r1z, fma(r0y, r1y, r0x * r1x));
     const double d12 = fma(r1z, r2z, fma(r1y, r2y, r1x * r2x));
     const double d20 = fma(r2z, r0z, fma(r2y, r0y, r2x * r0x));
-    const double d01 = fma(r0z, r1z, fma(r0y, r1y, r0x * r1x));
-    const double den = fma(l2, d01, fma(l1, d20, fma(l0, d12, (l0 * l1) * l2)));
-    const double num = hp * fld(24);
-    const double G0 = fld(21), G1 = fld(22), G2 = fld(23);
-    // (measured alternatives, both slower: a shorter far-field series tier -- near- and far-side faces share a
-    //  warp, so both tiers execute -- and computing the common path unconditionally -- register pressure)
-    double ln0, ln1, ln2, om;
-    bool fast = (den > 0.0) && (fabs(num) <= 0.1 * den);
+    const double d03 = fma(r0z, r3z, fma(r0y, r3y, r0x * r3x));
+    const double d31 = fma(r3z, r1z, fma(r3y, r1y, r3x * r1x));
+    const double l01 = l0 * l1;
+    const double denA = fma(l2, d01, fma(l1, d20, fma(l0, d12, l01 * l2)));
+    const double denB = fma(l3, d01, fma(l0, d31, fma(l1, d03, l01 * l3)));
+    const double numA = hpA * fld(41), numB = hpB * fld(42);
+    const double G0 = fld(36), G1 = fld(37), G2 = fld(38), G3 = fld(39), G4 = fld(40);
+    double ln0, ln1, ln2, ln3, ln4, omA, omB;
+    bool fast = (denA > 0.0) && (denB > 0.0) && (fabs(numA) <= 0.1 * denA) && (fabs(numB) <= 0.1 * denB);
     if (fast) {
-        const double P01 = A0 * A1, P2D = A2 * den;
-        const double inv = tm_div(1.0, P01 * P2D);
-        const double i01 = P2D * inv, i2D = P01 * inv;
-        const double z0 = (G0 * A1) * i01, z1 = (G1 * A0) * i01, z2 = (G2 * den) * i2D;
-        const double q = (num * A2) * i2D;
-        const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2;
-        fast = (z0s < 0.04) && (z1s < 0.04) && (z2s < 0.04);
+        const double P01 = a0 * a1, P2A = a2 * denA, P34 = a3 * a4;
+        const double X = P01 * P2A, Y = P34 * denB;
+        const double inv = tm_div(1.0, X * Y);
+        const double iX = Y * inv, iY = X * inv;
+        const double i01 = P2A * iX, i2A = P01 * iX, i34 = denB * iY, iB = P34 * iY;
+        const double z0 = (G0 * a1) * i01, z1 = (G1 * a0) * i01, z2 = (G2 * denA) * i2A;
+        const double qA = (numA * a2) * i2A;
+        const double z3 = (G3 * a4) * i34, z4 = (G4 * a3) * i34;
+        const double qB = numB * iB;
+        const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
+        fast = (z0s < 0.04) && (z1s < 0.04) && (z2s < 0.04) && (z3s < 0.04) && (z4s < 0.04);
         if (fast) {
-            ln0 = tm_two_atanh_series_n<11>(z0, z0s);
-            ln1 = tm_two_atanh_series_n<11>(z1, z1s);
-            ln2 = tm_two_atanh_series_n<11>(z2, z2s);
-            om = 2.0 * tm_atan_series_n<8>(q, q * q);
+            ln0 = tm_two_atanh_mm(z0, z0s);
+            ln1 = tm_two_atanh_mm(z1, z1s);
+            ln2 = tm_two_atanh_mm(z2, z2s);
+            ln3 = tm_two_atanh_mm(z3, z3s);
+            ln4 = tm_two_atanh_mm(z4, z4s);
+            omA = tm_two_atan_mm(qA, qA * qA);
+            omB = tm_two_atan_mm(qB, qB * qB);
         }
     }
-    if (!fast) {   // face close to the field point: separate divisions, ln-based atanh, full-range atan2
-        ln0 = tm_two_atanh(tm_div(G0, A0));
-        ln1 = tm_two_atanh(tm_div(G1, A1));
-        ln2 = tm_two_atanh(tm_div(G2, A2));
-        om = 2.0 * tm_atan2(num, den);
+    if (!fast) {   // a face close to the field point: separate divisions, ln-based atanh, full-range atan2
+        ln0 = tm_two_atanh(tm_div(G0, a0));
+        ln1 = tm_two_atanh(tm_div(G1, a1));
+        ln2 = tm_two_atanh(tm_div(G2, a2));
+        ln3 = tm_two_atanh(tm_div(G3, a3));
+        ln4 = tm_two_atanh(tm_div(G4, a4));
+        omA = 2.0 * tm_atan2(numA, denA);
+        omB = 2.0 * tm_atan2(numB, denB);
     }
-    hp_out = hp;
-    return fma(-hp, om, fma(hq2, ln2, fma(hq1, ln1, hq0 * ln0)));
+    hpA_out = hpA;
+    hpB_out = hpB;
+    SA = fma(-hpA, omA, fma(hA2, ln2, fma(hA1, ln1, hA0 * ln0)));
+    SB = fma(-hpB, omB, fma(hB2, ln4, fma(hB1, ln3, hB0 * ln0)));
 }
 
-// One face, one field point: acc += N_p S_p (and pot += hp S_p).
+// acc += N_A S_A + N_B S_B (and pot += hp_A S_A + hp_B S_B)
 template <bool kPot, class Fld>
-__device__ __forceinline__ void face_term(Fld fld, double Px, double Py, double Pz, double &ax, double &ay,
+__device__ __forceinline__ void pair_term(Fld fld, double Px, double Py, double Pz, double &ax, double &ay,
                                           double &az, double &pot)
 {
-    double hp;
-    const double S = face_S(fld, Px, Py, Pz, hp);
-    ax = fma(fld(9), S, ax);
-    ay = fma(fld(10), S, ay);
-    az = fma(fld(11), S, az);
-    if (kPot) pot = fma(hp, S, pot);
+    double SA, SB, hpA, hpB;
+    pair_S(fld, Px, Py, Pz, SA, SB, hpA, hpB);
+    ax = fma(fld(15), SB, fma(fld(12), SA, ax));
+    ay = fma(fld(16), SB, fma(fld(13), SA, ay));
+    az = fma(fld(17), SB, fma(fld(14), SA, az));
+    if (kPot) pot = fma(hpB, SB, fma(hpA, SA, pot));
 }
 
 // mesh_utility.py:132-166: Moeller-Trumbore with ray direction (0,0,1) (:83).  Every rounding is the

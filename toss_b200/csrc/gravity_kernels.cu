@@ -1,27 +1,30 @@
 // toss_b200/csrc/gravity_kernels.cu -- K1: batched polyhedral gravity; batched RHS; point-in-polyhedron; DFMA peak.
+#include <stdlib.h>
+
 #include "gravity.cuh"
 
 // ------------------------------------------------------------------------------------------------
-// K1a  thread-per-point.  One CTA = 128 field points.  The face records (AoS, 208 B) stream through a
-// 4-stage shared-memory ring filled by TMA bulk copies (one 13 KB tile = 64 faces per copy); every
+// K1a  thread-per-point.  One CTA = 128 field points.  The pair records (AoS, 352 B) stream through a
+// 4-stage shared-memory ring filled by TMA bulk copies (one 11 KB tile = 32 pairs per copy); every
 // lane reads the SAME record (LDS.128 broadcast), so there is no reduction at all: each thread owns
-// its accumulator.  FP64-pipe bound: ~1 smem wavefront per ~20 DFMA-pipe instructions.
+// its accumulator.  FP64-pipe bound: ~1 smem wavefront per ~10 DFMA-pipe instructions.
 // ------------------------------------------------------------------------------------------------
 constexpr int kK1Threads = 128;
 constexpr int kK1Stages = 4;
-constexpr int kAosTileBytes = kAosTileFaces * kAosStride * 8;
+constexpr int kPairTileBytes = kPairAosTile * kPairAosStride * 8;
 
 template <bool kPot>
 __global__ void __launch_bounds__(kK1Threads, 4)
-gravity_points_kernel(const double *__restrict__ face_aos, int n_tiles, int last_tile_faces,
-                      const double *__restrict__ pts, int64_t n,
-                      double *__restrict__ acc, double *__restrict__ pot, double Grho)
+gravity_points_kernel(const double *__restrict__ pair_aos, int n_tiles, int last_tile_pairs,
+                           const double *__restrict__ pts, int64_t n,
+                           double *__restrict__ acc, double *__restrict__ pot, double Grho)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *tiles = reinterpret_cast<double *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kK1Stages * kAosTileBytes);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kK1Stages * kPairTileBytes);
     uint64_t *empty = full + kK1Stages;
     const int tid = threadIdx.x, lane = tid & 31;
+    constexpr int kTileDoubles = kPairAosTile * kPairAosStride;
 
     if (tid == 0) {
         for (int s = 0; s < kK1Stages; ++s) {
@@ -34,9 +37,8 @@ gravity_points_kernel(const double *__restrict__ face_aos, int n_tiles, int last
     if (tid == 0) {
         const int pre = n_tiles < kK1Stages ? n_tiles : kK1Stages;
         for (int s = 0; s < pre; ++s) {
-            mbar_arrive_expect_tx(&full[s], kAosTileBytes);
-            tma_load_1d(tiles + (size_t)s * kAosTileFaces * kAosStride, face_aos + (size_t)s * kAosTileFaces * kAosStride,
-                        kAosTileBytes, &full[s]);
+            mbar_arrive_expect_tx(&full[s], kPairTileBytes);
+            tma_load_1d(tiles + (size_t)s * kTileDoubles, pair_aos + (size_t)s * kTileDoubles, kPairTileBytes, &full[s]);
         }
     }
 
@@ -48,24 +50,23 @@ gravity_points_kernel(const double *__restrict__ face_aos, int n_tiles, int last
     for (int it = 0; it < n_tiles; ++it) {
         const int s = it % kK1Stages;
         const uint32_t ph = (uint32_t)(it / kK1Stages) & 1u;
-        // refill the stage consumed one iteration ago (gives the other warps a whole tile to release it)
         if (tid == 0 && it >= 1) {
             const int prev = it - 1, nxt = prev + kK1Stages;
             if (nxt < n_tiles) {
                 const int ps = prev % kK1Stages;
                 mbar_wait(&empty[ps], (uint32_t)(prev / kK1Stages) & 1u);
-                mbar_arrive_expect_tx(&full[ps], kAosTileBytes);
-                tma_load_1d(tiles + (size_t)ps * kAosTileFaces * kAosStride,
-                            face_aos + (size_t)nxt * kAosTileFaces * kAosStride, kAosTileBytes, &full[ps]);
+                mbar_arrive_expect_tx(&full[ps], kPairTileBytes);
+                tma_load_1d(tiles + (size_t)ps * kTileDoubles, pair_aos + (size_t)nxt * kTileDoubles, kPairTileBytes,
+                            &full[ps]);
             }
         }
         mbar_wait(&full[s], ph);
-        const double *tile = tiles + (size_t)s * kAosTileFaces * kAosStride;
-        const int f_end = (it == n_tiles - 1) ? last_tile_faces : kAosTileFaces;   // skip the padding records
-#pragma unroll 2
-        for (int f = 0; f < f_end; ++f) {
-            const double *rec = tile + f * kAosStride;
-            face_term<kPot>([rec](int k) { return rec[k]; }, Px, Py, Pz, ax, ay, az, pv);
+        const double *tile = tiles + (size_t)s * kTileDoubles;
+        const int p_end = (it == n_tiles - 1) ? last_tile_pairs : kPairAosTile;
+#pragma unroll 1
+        for (int f = 0; f < p_end; ++f) {
+            const double *rec = tile + f * kPairAosStride;
+            pair_term<kPot>([rec](int k) { return rec[k]; }, Px, Py, Pz, ax, ay, az, pv);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -80,17 +81,17 @@ gravity_points_kernel(const double *__restrict__ face_aos, int n_tiles, int last
 
 // ------------------------------------------------------------------------------------------------
 // K1b  warp-per-point (few points: the single-point `evaluable(x)` call, compute_motion batches):
-// lanes stride the faces of the flat SoA (coalesced 256 B loads), butterfly-shuffle reduction.
+// lanes stride the pair records of the flat SoA (coalesced 256 B loads), butterfly-shuffle reduction.
 // Same lane->face map and reduction tree as the stepper, so values are identical to the RHS it sees.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_gravity_global(const double *__restrict__ soa, int Fpad32, double Px, double Py,
+__device__ __forceinline__ void warp_gravity_global(const double *__restrict__ soa, int Ppad32, double Px, double Py,
                                                     double Pz, int lane, double &ax, double &ay, double &az,
                                                     double &pv)
 {
     ax = ay = az = pv = 0.0;
-    for (int f = lane; f < Fpad32; f += 32) {
+    for (int f = lane; f < Ppad32; f += 32) {
         const double *col = soa + f;
-        face_term<true>([col, Fpad32](int k) { return __ldg(col + (size_t)k * Fpad32); }, Px, Py, Pz, ax, ay, az, pv);
+        pair_term<true>([col, Ppad32](int k) { return __ldg(col + (size_t)k * Ppad32); }, Px, Py, Pz, ax, ay, az, pv);
     }
     ax = warp_sum(ax);
     ay = warp_sum(ay);
@@ -98,7 +99,7 @@ __device__ __forceinline__ void warp_gravity_global(const double *__restrict__ s
     pv = warp_sum(pv);
 }
 
-__global__ void __launch_bounds__(256) gravity_warp_kernel(const double *__restrict__ soa, int Fpad32,
+__global__ void __launch_bounds__(256) gravity_warp_kernel(const double *__restrict__ soa, int Ppad32,
                                                            const double *__restrict__ pts, int64_t n,
                                                            double *__restrict__ acc, double *__restrict__ pot,
                                                            double Grho)
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) gravity_warp_kernel(const double *__restr
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n) return;
     double ax, ay, az, pv;
-    warp_gravity_global(soa, Fpad32, pts[3 * w], pts[3 * w + 1], pts[3 * w + 2], lane, ax, ay, az, pv);
+    warp_gravity_global(soa, Ppad32, pts[3 * w], pts[3 * w + 1], pts[3 * w + 2], lane, ax, ay, az, pv);
     if (lane == 0) {
         acc[3 * w] = Grho * ax;
         acc[3 * w + 1] = Grho * ay;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) gravity_warp_kernel(const double *__restr
 }
 
 // equations_of_motion.py:62-95 for a batch of (t, y): rotate r by -w t, gravity there, NOT rotated back.
-__global__ void __launch_bounds__(256) compute_motion_kernel(const double *__restrict__ soa, int Fpad32, double Grho,
+__global__ void __launch_bounds__(256) compute_motion_kernel(const double *__restrict__ soa, int Ppad32, double Grho,
                                                              UnitAxis k, double w, int rotate,
                                                              const double *__restrict__ ts,
                                                              const double *__restrict__ ys, int64_t n,
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256) compute_motion_kernel(const double *__res
     double px = y[0], py = y[1], pz = y[2];
     if (rotate) rotate_point_dev(ts[i], y[0], y[1], y[2], k.x, k.y, k.z, w, px, py, pz);
     double ax, ay, az, pv;
-    warp_gravity_global(soa, Fpad32, px, py, pz, lane, ax, ay, az, pv);
+    warp_gravity_global(soa, Ppad32, px, py, pz, lane, ax, ay, az, pv);
     if (lane == 0) {
         double *o = out + 6 * i;
         o[0] = y[3];
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 
 // tmath.cuh functions by id, for the bit-parity tests:
 // 0 two_atanh 1 log 2 atan2(a,b) 3 sincos 4 root8 5 root4 6 atan series (8 terms) 7 a/b 8 sqrt
+// 9 2 atanh minimax (z*z <= 0.04) 10 2 atan minimax (t*t <= 0.01)
 __global__ void math_probe_kernel(int fn, const double *__restrict__ a, const double *__restrict__ b, int64_t n,
                                   double *__restrict__ out, double *__restrict__ out2)
 {
@@ -215,6 +217,8 @@ __global__ void math_probe_kernel(int fn, const double *__restrict__ a, const do
     case 6: r = tm_atan_series<8>(a[i]); break;
     case 7: r = tm_div(a[i], b[i]); break;
     case 8: r = tm_sqrt(a[i]); break;
+    case 9: r = tm_two_atanh_mm(a[i], a[i] * a[i]); break;
+    case 10: r = tm_two_atan_mm(a[i], a[i] * a[i]); break;
     default: r = __longlong_as_double(0x7ff8000000000000LL);
     }
     out[i] = r;
@@ -271,29 +275,28 @@ int launch_div_sqrt_selftest(toss_ctx *ctx, int64_t samples, int64_t *bad_div, i
 
 int launch_gravity(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc, double *d_pot, cudaStream_t st)
 {
-    TOSS_REQUIRE(ctx && ctx->d_face_aos, "toss_gravity_eval: no mesh uploaded");
+    TOSS_REQUIRE(ctx && ctx->d_pair_aos, "toss_gravity_eval: no mesh uploaded");
     if (n <= 0) return 0;
     if (n < 4096) {   // not enough points to fill the machine with one thread each
         const int64_t threads = n * 32;
         const int64_t blocks = (threads + 255) / 256;
-        gravity_warp_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_face_soa, ctx->Fpad32, d_pts, n, d_acc, d_pot,
+        gravity_warp_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_pair_soa, ctx->Ppad32, d_pts, n, d_acc, d_pot,
                                                             ctx->Grho);
     } else {
-        const size_t smem = (size_t)kK1Stages * kAosTileBytes + 2 * kK1Stages * sizeof(uint64_t);
+        const size_t smem = (size_t)kK1Stages * kPairTileBytes + 2 * kK1Stages * sizeof(uint64_t);
         const int64_t blocks = (n + kK1Threads - 1) / kK1Threads;
         TOSS_REQUIRE(blocks < 2147483647LL, "toss_gravity_eval: too many points for one launch");
+        const int last = ctx->n_pairs - (ctx->n_pair_aos_tiles - 1) * kPairAosTile;   // skip the padding records
         if (d_pot) {
             TOSS_CHECK_CUDA(cudaFuncSetAttribute(gravity_points_kernel<true>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gravity_points_kernel<true><<<(unsigned)blocks, kK1Threads, smem, st>>>(
-                ctx->d_face_aos, ctx->n_aos_tiles, ctx->F - (ctx->n_aos_tiles - 1) * kAosTileFaces, d_pts, n, d_acc, d_pot,
-                ctx->Grho);
+                ctx->d_pair_aos, ctx->n_pair_aos_tiles, last, d_pts, n, d_acc, d_pot, ctx->Grho);
         } else {
             TOSS_CHECK_CUDA(cudaFuncSetAttribute(gravity_points_kernel<false>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             gravity_points_kernel<false><<<(unsigned)blocks, kK1Threads, smem, st>>>(
-                ctx->d_face_aos, ctx->n_aos_tiles, ctx->F - (ctx->n_aos_tiles - 1) * kAosTileFaces, d_pts, n, d_acc, nullptr,
-                ctx->Grho);
+                ctx->d_pair_aos, ctx->n_pair_aos_tiles, last, d_pts, n, d_acc, nullptr, ctx->Grho);
         }
     }
     ctx->launches++;
@@ -304,10 +307,10 @@ int launch_gravity(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc,
 int launch_compute_motion(toss_ctx *ctx, const toss_params *p, const double *d_t, const double *d_y, int64_t n,
                           double *d_out, cudaStream_t st)
 {
-    TOSS_REQUIRE(ctx && ctx->d_face_soa, "toss_compute_motion: no mesh uploaded");
+    TOSS_REQUIRE(ctx && ctx->d_pair_soa, "toss_compute_motion: no mesh uploaded");
     if (n <= 0) return 0;
     const int64_t blocks = (n * 32 + 255) / 256;
-    compute_motion_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_face_soa, ctx->Fpad32, ctx->Grho,
+    compute_motion_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_pair_soa, ctx->Ppad32, ctx->Grho,
                                                           unit_axis_host(p->spin_axis), p->spin_velocity,
                                                           p->activate_rotation, d_t, d_y, n, d_out);
     ctx->launches++;
@@ -317,10 +320,10 @@ int launch_compute_motion(toss_ctx *ctx, const toss_params *p, const double *d_t
 
 int launch_is_outside(toss_ctx *ctx, const double *d_pts, int64_t n, uint8_t *d_out, cudaStream_t st)
 {
-    TOSS_REQUIRE(ctx && ctx->d_face_soa, "toss_is_outside: no mesh uploaded");
+    TOSS_REQUIRE(ctx && ctx->d_ray_soa, "toss_is_outside: no mesh uploaded");
     if (n <= 0) return 0;
     const int64_t blocks = (n * 32 + 255) / 256;
-    is_outside_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_face_soa, ctx->Fpad32, d_pts, n, d_out);
+    is_outside_kernel<<<(unsigned)blocks, 256, 0, st>>>(ctx->d_ray_soa, ctx->Fpad32, d_pts, n, d_out);
     ctx->launches++;
     TOSS_CHECK_CUDA(cudaGetLastError());
     return 0;

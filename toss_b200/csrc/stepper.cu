@@ -5,18 +5,18 @@
 // (toss/trajectory/compute_trajectory.py:13-162, 203-261) for a whole population.
 //
 // One warp per trajectory.  Lanes 0..5 own the six state components (y_c, k_j[c]); for every RHS
-// evaluation the 32 lanes split the faces (lane -> faces lane, lane+32, ...), accumulate in a fixed
+// evaluation the 32 lanes split the face pairs (lane -> pair records lane, lane+32, ...), accumulate in a fixed
 // order and butterfly-reduce, so a trajectory's arithmetic does not depend on the population around
 // it.  Warps pull trajectories from an atomic queue and retire them independently (finished, step
 // cap, non-finite state, knot capacity).
 //
 // Two mesh-staging modes:
-//   RESIDENT  the flat SoA face table fits in shared memory (lllp, llp): TMA-copied once per CTA;
+//   RESIDENT  the flat SoA pair table fits in shared memory (lllp, llp): TMA-copied once per CTA;
 //             warps then run completely independently.
-//   STREAM    (lp, full) the table streams through a 3-stage ring of 25.6 KB SoA tiles filled by TMA
-//             bulk copies (mbarrier full/empty pairs); the 8 warps of a CTA consume the same tile
+//   STREAM    (lp, full) the table streams through a 3-stage ring of 44 KB SoA tiles (128 pairs) filled by TMA
+//             bulk copies (mbarrier full/empty pairs); the 16 warps of a CTA consume the same tile
 //             sequence, one RHS evaluation per warp per sweep, coupled only through the ring (a warp can
-//             run at most two tiles ahead), so every byte fetched from L2 is used by 8 trajectories.
+//             run at most two tiles ahead), so every byte fetched from L2 is used by 16 trajectories.
 //             There is no CTA-wide barrier after start-up: warps retire from the ring with arrive_drop.
 #include <stdlib.h>
 
@@ -26,31 +26,33 @@
 #include "rk8713m_tableau.h"
 
 #ifndef K2_WARPS
-#define K2_WARPS 8
+#define K2_WARPS 16
 #endif
 #ifndef K2_STAGES
 #define K2_STAGES 3
 #endif
 #ifndef K2_MINBLOCKS
-#define K2_MINBLOCKS 2
+#define K2_MINBLOCKS 1
 #endif
 #ifndef K2_UNROLL
-#define K2_UNROLL 2
+#define K2_UNROLL 1
 #endif
 constexpr int kK2Warps = K2_WARPS;
 constexpr int kK2Threads = kK2Warps * 32;
 constexpr int kK2Stages = K2_STAGES;
 constexpr int kK2Unroll = K2_UNROLL;
 constexpr int kK2BarSlots = 2 * K2_STAGES + 2 + (K2_STAGES + 2) / 2;   // full[] | empty[] | live + claim[] (ints) | pad
-constexpr int kSoaTileBytes = kSoaTileDoubles * 8;
+constexpr int kPairTileBytes = kPairTileDoubles * 8;
 
 struct StepArgs {
     toss_params p;
     UnitAxis axis;
     double Grho;
-    const double *face_soa;    // [25][Fpad32]           (RESIDENT)
-    const double *face_tiles;  // [n_tiles][25][128]     (STREAM)
-    int Fpad32, n_tiles, last_tile_faces;   // last_tile_faces: real faces of the last tile rounded up to 32
+    const double *pair_soa;    // [43][Ppad32]           (RESIDENT)
+    const double *pair_tiles;  // [n_tiles][43][128]     (STREAM)
+    const double *ray_soa;     // [9][Fpad32] faces in mesh order (global memory): the event-point ray test
+    int Ppad32, n_tiles, last_tile_pairs;   // last_tile_pairs: real pairs of the last tile rounded up to 32
+    int Fpad32;
     const double *x;           // pop x dim
     int pop, dim, n_fixed, n_man, knot_cap;
     double fixed[8];
@@ -58,7 +60,7 @@ struct StepArgs {
     double *knots_t, *knots_y, *knots_f, *intervals;
     int32_t *seg_start, *n_seg, *collision, *queue;
     const int32_t *order;      // queue position -> trajectory index (longest predicted first), or NULL
-    int proxy_n;               // PROXY instantiation: number of mascons (face_soa then points at [n][4] x y z G*m)
+    int proxy_n;               // PROXY instantiation: number of mascons (pair_soa then points at [n][4] x y z G*m)
     double proxy_soft2;
     int32_t *proxy_cost;       // PROXY: predicted RHS count per trajectory
     toss_counters *counters;
@@ -69,7 +71,7 @@ __host__ __device__ inline int warp_state_doubles(int n_man) { return 6 + 78 + 2
 
 // Called by lane 0 of a warp right after it arrived on empty[s] for tile `it`: if that arrival completed the phase
 // (every warp still in the ring has released the tile), claim the refill and issue the TMA load of tile it + stages.
-__device__ __forceinline__ void refill_if_released(uint64_t *bars, int *claim, double *mesh, const double *face_tiles,
+__device__ __forceinline__ void refill_if_released(uint64_t *bars, int *claim, double *mesh, const double *pair_tiles,
                                                    int n_tiles, int s, uint32_t it)
 {
     uint32_t done;
@@ -81,19 +83,19 @@ __device__ __forceinline__ void refill_if_released(uint64_t *bars, int *claim, d
         : "r"(smem_u32(&bars[kK2Stages + s])), "r"((it / kK2Stages) & 1u)
         : "memory");
     if (done && atomicMax(&claim[s], (int)it) < (int)it) {
-        mbar_arrive_expect_tx(&bars[s], kSoaTileBytes);
-        tma_load_1d(mesh + (size_t)s * kSoaTileDoubles,
-                    face_tiles + (size_t)((it + kK2Stages) % (uint32_t)n_tiles) * kSoaTileDoubles, kSoaTileBytes, &bars[s]);
+        mbar_arrive_expect_tx(&bars[s], kPairTileBytes);
+        tma_load_1d(mesh + (size_t)s * kPairTileDoubles,
+                    pair_tiles + (size_t)((it + kK2Stages) % (uint32_t)n_tiles) * kPairTileDoubles, kPairTileBytes, &bars[s]);
     }
 }
 
 // Teams (kTeam = 2 or 4 warps per trajectory) are for populations too small to fill the machine with one warp
 // each (or to keep its tail short).  The owner warp (rank 0) runs the state machine; every warp of the team computes
-// the per-face scalar S_p for its share of the 32-face rows of a tile (rows rank, rank + kTeam, ...) into a shared
-// buffer; after a team barrier the owner adds N_p S_p in the canonical order (row 0, 1, 2, ... of every tile).  The
+// the per-face scalars S_A, S_B for its share of the 32-pair rows of a tile (rows rank, rank + kTeam, ...) into a
+// shared buffer; after a team barrier the owner adds N_A S_A + N_B S_B in the canonical order (row 0, 1, 2, ... of every tile).  The
 // arithmetic, and therefore every result bit, is the same for any team size.
 enum : int { kModeGrav = 0, kModeSkip = 1, kModeRetire = 2 };
-constexpr int kTeamBufDoubles = 4 + 2 * 4 * 32;   // P[3] + mode | S[2 buffers][4 rows][32 lanes]
+constexpr int kTeamBufDoubles = 4 + 2 * 4 * 64;   // P[3] + mode | S[2 buffers][4 rows][S_A x 32 lanes | S_B x 32 lanes]
 
 __device__ __forceinline__ void team_bar(int team, int nthreads)
 {
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int team = wid / kTeam, rank = wid % kTeam;
-    const int mesh_doubles = kProxy ? 4 * a.proxy_n : (kStream ? kK2Stages * kSoaTileDoubles : kFaceFields * a.Fpad32);
+    const int mesh_doubles = kProxy ? 4 * a.proxy_n : (kStream ? kK2Stages * kPairTileDoubles : kPairFields * a.Ppad32);
     double *mesh = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(mesh + mesh_doubles);   // full[3] empty[3] (STREAM) / full[1]
     double *wstate = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)wid * warp_state_doubles(a.n_man);
@@ -139,9 +141,9 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     if (tid == 0) {
         if (kStream) {
             for (int s = 0; s < kK2Stages; ++s) {   // the ring is cyclic over the mesh: always something to fetch
-                mbar_arrive_expect_tx(&bars[s], kSoaTileBytes);
-                tma_load_1d(mesh + (size_t)s * kSoaTileDoubles,
-                            a.face_tiles + (size_t)(s % a.n_tiles) * kSoaTileDoubles, kSoaTileBytes, &bars[s]);
+                mbar_arrive_expect_tx(&bars[s], kPairTileBytes);
+                tma_load_1d(mesh + (size_t)s * kPairTileDoubles,
+                            a.pair_tiles + (size_t)(s % a.n_tiles) * kPairTileDoubles, kPairTileBytes, &bars[s]);
             }
         } else {
             const uint32_t bytes = (uint32_t)mesh_doubles * 8u;
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
             while (off < bytes) {
                 const uint32_t c = bytes - off < 65536u ? bytes - off : 65536u;
                 tma_load_1d(reinterpret_cast<unsigned char *>(mesh) + off,
-                            reinterpret_cast<const unsigned char *>(a.face_soa) + off, c, &bars[0]);
+                            reinterpret_cast<const unsigned char *>(a.pair_soa) + off, c, &bars[0]);
                 off += c;
             }
         }
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                         if (lane == 0) {
                             const uint32_t nxt = it + (uint32_t)((s + kK2Stages - (int)(it % kK2Stages)) % kK2Stages);
                             mbar_arrive_drop(&bars[kK2Stages + s]);
-                            refill_if_released(bars, claim, mesh, a.face_tiles, a.n_tiles, s, nxt);
+                            refill_if_released(bars, claim, mesh, a.pair_tiles, a.n_tiles, s, nxt);
                         }
                     }
                     __syncwarp();
@@ -187,15 +189,16 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
             if (kStream) {
                 for (int tl = 0; tl < a.n_tiles; ++tl, ++it) {
                     const int s = it % kK2Stages;
-                    const int rows = ((tl == a.n_tiles - 1) ? a.last_tile_faces : kSoaTileFaces) >> 5;
+                    const int rows = ((tl == a.n_tiles - 1) ? a.last_tile_pairs : kPairTile) >> 5;
                     mbar_wait(&bars[s], (it / kK2Stages) & 1u);
                     if (mode == kModeGrav) {
-                        const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
+                        const double *tile = mesh + (size_t)s * kPairTileDoubles + lane;
                         for (int r = rank; r < rows; r += kTeam) {
                             const double *col = tile + 32 * r;
-                            double hp;
-                            sbuf[(spar * 4 + r) * 32 + lane] =
-                                face_S([col](int k) { return col[k * kSoaTileFaces]; }, Px, Py, Pz, hp);
+                            double SA, SB, hpA, hpB;
+                            pair_S([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, SA, SB, hpA, hpB);
+                            sbuf[(spar * 4 + r) * 64 + lane] = SA;
+                            sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                         }
                         team_bar(team, 32 * kTeam);   // S of this tile complete; the owner accumulates
                         spar ^= 1;
@@ -203,17 +206,19 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     __syncwarp();
                     if (lane == 0) {
                         mbar_arrive(&bars[kK2Stages + s]);
-                        refill_if_released(bars, claim, mesh, a.face_tiles, a.n_tiles, s, it);
+                        refill_if_released(bars, claim, mesh, a.pair_tiles, a.n_tiles, s, it);
                     }
                 }
             } else if (mode == kModeGrav) {
-                const int Fp = a.Fpad32, rows_total = Fp >> 5;
+                const int Fp = a.Ppad32, rows_total = Fp >> 5;
                 for (int v = 0; v * 4 < rows_total; ++v) {
                     const int rows = rows_total - 4 * v < 4 ? rows_total - 4 * v : 4;
                     for (int r = rank; r < rows; r += kTeam) {
                         const double *col = mesh + 32 * (4 * v + r) + lane;
-                        double hp;
-                        sbuf[(spar * 4 + r) * 32 + lane] = face_S([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, hp);
+                        double SA, SB, hpA, hpB;
+                        pair_S([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, SA, SB, hpA, hpB);
+                        sbuf[(spar * 4 + r) * 64 + lane] = SA;
+                        sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                     }
                     team_bar(team, 32 * kTeam);
                     spar ^= 1;
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                         // the phase this arrival belongs to: the first tile >= tile_it that lives in stage s
                         const uint32_t nxt = tile_it + (uint32_t)((s + kK2Stages - (int)(tile_it % kK2Stages)) % kK2Stages);
                         mbar_arrive_drop(&bars[kK2Stages + s]);
-                        refill_if_released(bars, claim, mesh, a.face_tiles, a.n_tiles, s, nxt);
+                        refill_if_released(bars, claim, mesh, a.pair_tiles, a.n_tiles, s, nxt);
                     }
                 }
                 __syncwarp();
@@ -388,8 +393,18 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         // (mesh_utility.py:70-89) ray-casts it.  Event points are rare (a few per close pass), so the test gets a
         // sweep of its own over the same tile stream instead of loading the hot loop's registers.
         int hits = 0;
+        if (!kProxy && active && ray_sweep) {
+            const int Fr = a.Fpad32;
+#pragma unroll 2
+            for (int f = lane; f < Fr; f += 32) {
+                const double *col = a.ray_soa + f;
+                hits += ray_hits_dev(qx, qy, qz, __ldg(col), __ldg(col + Fr), __ldg(col + 2 * Fr), __ldg(col + 3 * Fr),
+                                     __ldg(col + 4 * Fr), __ldg(col + 5 * Fr), __ldg(col + 6 * Fr), __ldg(col + 7 * Fr),
+                                     __ldg(col + 8 * Fr));
+            }
+        }
 
-        // ------------------------------------------------ gravity sweep over all faces
+        // ------------------------------------------------ gravity sweep over all face pairs
         double ax = 0.0, ay = 0.0, az = 0.0, pv = 0.0;
         if (kProxy) {
             for (int m = lane; m < a.proxy_n; m += 32) {
@@ -403,8 +418,8 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         } else if (kStream) {
             for (int tl = 0; tl < a.n_tiles; ++tl, ++tile_it) {
                 const int s = tile_it % kK2Stages;
-                // rows of 32 faces in this tile that hold real faces (the last tile is only partly filled)
-                const int f_end = (tl == a.n_tiles - 1) ? a.last_tile_faces : kSoaTileFaces;
+                // rows of 32 pairs in this tile that hold real pairs (the last tile is only partly filled)
+                const int f_end = (tl == a.n_tiles - 1) ? a.last_tile_pairs : kPairTile;
 #ifdef K2_PROFILE
                 const long long c0 = clock64();
 #endif
@@ -416,38 +431,33 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 if (!active) prof_idle += c1 - c0;
 #endif
                 if (active && ray_sweep) {
-                    const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
-                    for (int f = 0; f < f_end; f += 32) {
-                        const double *col = tile + f;
-                        hits += ray_hits_dev(qx, qy, qz, col[0], col[kSoaTileFaces], col[2 * kSoaTileFaces],
-                                             col[3 * kSoaTileFaces], col[4 * kSoaTileFaces], col[5 * kSoaTileFaces],
-                                             col[6 * kSoaTileFaces], col[7 * kSoaTileFaces], col[8 * kSoaTileFaces]);
-                    }
+                    // the ray test ran on the global face table above; this sweep only keeps step with the ring
                 } else if (active && kTeam > 1) {
-                    // team sweep: S_p of my rows into the buffer, barrier, then N_p S_p of ALL rows in canonical order
-                    const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
+                    // team sweep: S of my rows into the buffer, barrier, then N S of ALL rows in canonical order
+                    const double *tile = mesh + (size_t)s * kPairTileDoubles + lane;
                     const int rows = f_end >> 5;
                     for (int r = 0; r < rows; r += kTeam) {
                         const double *col = tile + 32 * r;
-                        double hp;
-                        sbuf[(spar * 4 + r) * 32 + lane] =
-                            face_S([col](int k) { return col[k * kSoaTileFaces]; }, Px, Py, Pz, hp);
+                        double SA, SB, hpA, hpB;
+                        pair_S([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, SA, SB, hpA, hpB);
+                        sbuf[(spar * 4 + r) * 64 + lane] = SA;
+                        sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                     }
                     team_bar(team, 32 * kTeam);
                     for (int r = 0; r < rows; ++r) {
                         const double *col = tile + 32 * r;
-                        const double S = sbuf[(spar * 4 + r) * 32 + lane];
-                        ax = fma(col[9 * kSoaTileFaces], S, ax);
-                        ay = fma(col[10 * kSoaTileFaces], S, ay);
-                        az = fma(col[11 * kSoaTileFaces], S, az);
+                        const double SA = sbuf[(spar * 4 + r) * 64 + lane], SB = sbuf[(spar * 4 + r) * 64 + 32 + lane];
+                        ax = fma(col[15 * kPairTile], SB, fma(col[12 * kPairTile], SA, ax));
+                        ay = fma(col[16 * kPairTile], SB, fma(col[13 * kPairTile], SA, ay));
+                        az = fma(col[17 * kPairTile], SB, fma(col[14 * kPairTile], SA, az));
                     }
                     spar ^= 1;
                 } else if (active) {
-                    const double *tile = mesh + (size_t)s * kSoaTileDoubles + lane;
+                    const double *tile = mesh + (size_t)s * kPairTileDoubles + lane;
 #pragma unroll kK2Unroll
                     for (int f = 0; f < f_end; f += 32) {
                         const double *col = tile + f;
-                        face_term<false>([col](int k) { return col[k * kSoaTileFaces]; }, Px, Py, Pz, ax, ay, az, pv);
+                        pair_term<false>([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, ax, ay, az, pv);
                     }
                 }
                 __syncwarp();
@@ -458,33 +468,31 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 // once -- no dedicated producer, no warp ever waits on another one's bookkeeping
                 if (lane == 0) {
                     mbar_arrive(&bars[kK2Stages + s]);
-                    refill_if_released(bars, claim, mesh, a.face_tiles, a.n_tiles, s, tile_it);
+                    refill_if_released(bars, claim, mesh, a.pair_tiles, a.n_tiles, s, tile_it);
                 }
             }
         } else {
-            const int Fp = a.Fpad32;
+            const int Fp = a.Ppad32;
             if (ray_sweep) {
-                for (int f = lane; f < Fp; f += 32) {
-                    const double *col = mesh + f;
-                    hits += ray_hits_dev(qx, qy, qz, col[0], col[Fp], col[2 * Fp], col[3 * Fp], col[4 * Fp], col[5 * Fp],
-                                         col[6 * Fp], col[7 * Fp], col[8 * Fp]);
-                }
+                // done above on the global face table
             } else if (kTeam > 1) {
                 const int rows_total = Fp >> 5;
                 for (int v = 0; v * 4 < rows_total; ++v) {
                     const int rows = rows_total - 4 * v < 4 ? rows_total - 4 * v : 4;
                     for (int r = 0; r < rows; r += kTeam) {
                         const double *col = mesh + 32 * (4 * v + r) + lane;
-                        double hp;
-                        sbuf[(spar * 4 + r) * 32 + lane] = face_S([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, hp);
+                        double SA, SB, hpA, hpB;
+                        pair_S([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, SA, SB, hpA, hpB);
+                        sbuf[(spar * 4 + r) * 64 + lane] = SA;
+                        sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                     }
                     team_bar(team, 32 * kTeam);
                     for (int r = 0; r < rows; ++r) {
                         const double *col = mesh + 32 * (4 * v + r) + lane;
-                        const double S = sbuf[(spar * 4 + r) * 32 + lane];
-                        ax = fma(col[9 * Fp], S, ax);
-                        ay = fma(col[10 * Fp], S, ay);
-                        az = fma(col[11 * Fp], S, az);
+                        const double SA = sbuf[(spar * 4 + r) * 64 + lane], SB = sbuf[(spar * 4 + r) * 64 + 32 + lane];
+                        ax = fma(col[15 * Fp], SB, fma(col[12 * Fp], SA, ax));
+                        ay = fma(col[16 * Fp], SB, fma(col[13 * Fp], SA, ay));
+                        az = fma(col[17 * Fp], SB, fma(col[14 * Fp], SA, az));
                     }
                     spar ^= 1;
                 }
@@ -492,7 +500,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 #pragma unroll kK2Unroll
                 for (int f = lane; f < Fp; f += 32) {
                     const double *col = mesh + f;
-                    face_term<false>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, ax, ay, az, pv);
+                    pair_term<false>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, ax, ay, az, pv);
                 }
             }
         }
@@ -720,7 +728,7 @@ int toss_workspace_layout_impl(int pop, int n_man, int knot_cap, toss_ws_layout 
 int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
                      int n_fixed, int n_man, void *d_ws, int knot_cap, cudaStream_t st)
 {
-    TOSS_REQUIRE(ctx && ctx->d_face_soa, "toss_propagate: no mesh uploaded");
+    TOSS_REQUIRE(ctx && ctx->d_pair_soa, "toss_propagate: no mesh uploaded");
     TOSS_REQUIRE(pop > 0 && dim >= 0 && n_fixed >= 0 && n_fixed <= 7, "toss_propagate: bad population shape");
     TOSS_REQUIRE(n_man >= 0 && n_man <= 64, "toss_propagate: number_of_maneuvers must be in [0, 64]");
     TOSS_REQUIRE(n_fixed + dim == 7 + 5 * n_man, "toss_propagate: n_fixed + dim != 7 + 5*number_of_maneuvers");
@@ -733,11 +741,13 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     a.p = *p;
     a.axis = unit_axis_host(p->spin_axis);
     a.Grho = ctx->Grho;
-    a.face_soa = ctx->d_face_soa;
-    a.face_tiles = ctx->d_face_tiles;
+    a.pair_soa = ctx->d_pair_soa;
+    a.pair_tiles = ctx->d_pair_tiles;
+    a.ray_soa = ctx->d_ray_soa;
+    a.Ppad32 = ctx->Ppad32;
     a.Fpad32 = ctx->Fpad32;
-    a.n_tiles = ctx->n_soa_tiles;
-    a.last_tile_faces = ctx->Fpad32 - (ctx->n_soa_tiles - 1) * kSoaTileFaces;
+    a.n_tiles = ctx->n_pair_tiles;
+    a.last_tile_pairs = ctx->Ppad32 - (ctx->n_pair_tiles - 1) * kPairTile;
     a.x = d_x;
     a.pop = pop;
     a.dim = dim;
@@ -772,12 +782,12 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     if (lpt) {
         int32_t *order = a.queue + 4, *cost = order + pop;
         StepArgs px = a;
-        px.face_soa = ctx->d_mascons;
+        px.pair_soa = ctx->d_mascons;
         px.proxy_n = ctx->n_mascons;
         px.proxy_soft2 = ctx->mascon_soft2;
         px.proxy_cost = cost;
         const size_t psmem = (size_t)4 * ctx->n_mascons * 8 + (size_t)kK2Warps * warp_state_doubles(n_man) * 8 +
-                             kK2BarSlots * 8 + (size_t)kK2Warps * kTeamBufDoubles * 8;
+                             kK2BarSlots * 8 + (size_t)(kK2Warps / 2) * kTeamBufDoubles * 8;
         int pctas = (pop + kK2Warps - 1) / kK2Warps;
         if (pctas > K2_MINBLOCKS * ctx->sm_count) pctas = K2_MINBLOCKS * ctx->sm_count;
         TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -790,9 +800,9 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     }
 
     const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 +
-                               (size_t)kK2Warps * kTeamBufDoubles * 8;
-    const size_t resident_bytes = (size_t)kFaceFields * ctx->Fpad32 * 8 + state_bytes;
-    const size_t stream_bytes = (size_t)kK2Stages * kSoaTileBytes + state_bytes;
+                               (size_t)(kK2Warps / 2) * kTeamBufDoubles * 8;
+    const size_t resident_bytes = (size_t)kPairFields * ctx->Ppad32 * 8 + state_bytes;
+    const size_t stream_bytes = (size_t)kK2Stages * kPairTileBytes + state_bytes;
     const bool resident = resident_bytes <= (size_t)(200 / K2_MINBLOCKS) * 1024;   // every CTA on an SM keeps its own copy
     const int per_cta = kK2Warps / team;
     int ctas = (pop + per_cta - 1) / per_cta;
