@@ -34,6 +34,8 @@ sys.path.insert(0, str(ROOT))
 W_FACE = 127            # algorithmic FP64 operations per face-point pair (each sqrt/div/log/atan = 1)
 FIXED_POS = np.array([-135.13402075, -4089.53592604, 6050.17636635])   # default_cfg.toml initial_x/y/z
 N_MAN = 2
+MESH_PATHS = {"lllp": "3dmeshes/churyumov-gerasimenko_lllp.pk", "llp": "3dmeshes/churyumov-gerasimenko_llp.pk",
+              "lp": "3dmeshes/churyumov-gerasimenko_lp.pk", "full": "3dmeshes/churyumov-gerasimenko.pk"}
 
 
 def init_like_population(pop: int, n_man: int, seed: int, final_time: float = 604800.0) -> np.ndarray:
@@ -162,7 +164,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from toss_b200 import _native as N
-    from oracle import oracle as O          # mesh loader + the cpu_baseline leg ONLY
+    import toss_b200 as T
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,10 +176,15 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     ctx = N.Context(local_rank)
-    v, f = O.load_mesh(args.mesh)
+    _, v, f, _ = T.create_mesh(MESH_PATHS[args.mesh])      # the package's own loader (mesh_utility.py:37-67)
+    f = np.ascontiguousarray(f, dtype=np.int32)
     F = len(f)
     ctx.upload_mesh(v, f, 533.0)
-    ctx.upload_grid(*O.default_grid())
+    targs = T.setup_parameters()
+    ctx.upload_grid(np.asarray(targs.problem.tensor_grid_r, dtype=np.float64),
+                    np.asarray(targs.problem.tensor_grid_theta, dtype=np.float64),
+                    np.asarray(targs.problem.tensor_grid_phi, dtype=np.float64),
+                    np.asarray(targs.problem.bool_tensor))
     # collided trajectories score the constant 1e30: the path retires them at the first event point inside the mesh
     # (identical fitness vector; the reference arm / cpu_baseline integrate them to the end, as the reference does)
     p = N.make_params(stop_on_collision=1)
@@ -207,11 +214,7 @@ def run_ours(args):
 
     # the user-facing call: the pygmo UDP's batch_fitness on HOST decision vectors (shards itself over the
     # process group, copies its shard H2D from pinned memory, runs the kernels, copies the fitness D2H, all-gathers)
-    import toss_b200 as T
-    targs = T.setup_parameters()
-    mesh_file = {"lllp": "churyumov-gerasimenko_lllp", "llp": "churyumov-gerasimenko_llp",
-                 "lp": "churyumov-gerasimenko_lp", "full": "churyumov-gerasimenko"}[args.mesh]
-    targs.mesh.mesh_path = f"3dmeshes/{mesh_file}.pk"
+    targs.mesh.mesh_path = MESH_PATHS[args.mesh]
     (targs.mesh.body, targs.mesh.vertices, targs.mesh.faces,
      targs.mesh.largest_body_protuberant) = T.create_mesh(targs.mesh.mesh_path)
     lb, ub = T.setup_initial_state_domain(FIXED_POS, targs.problem.start_time, targs.problem.final_time, N_MAN,
@@ -321,6 +324,7 @@ def run_ours(args):
             line["gravity_microbench"] = gravity_microbench(ctx, F, fp64_peak)
             line["converged_like"] = converged_like(ctx, N, p, args, torch, F, fp64_peak)
         if not args.no_cpu_baseline:
+            from oracle import oracle as O      # the cpu_baseline leg: the only use of oracle/ in this arm
             line["cpu_baseline"] = cpu_baseline(O, args, xs_all)
         emit(line)
     if world > 1:

@@ -75,6 +75,28 @@ def test_gravity_vs_mpmath(name, npts, tol):
         assert np.linalg.norm(d[i] - truth) / nt < 5e-12
 
 
+def test_gravity_near_the_surface_vs_mpmath():
+    """Points 3 m .. 600 m above face centroids: some edge / solid-angle terms of the nearby pairs are outside the
+    range of the short polynomials and fall back, each on its own, to the ln-based atanh / full-range atan2
+    (pair_term); far terms of the same pair stay on the shared division.  Every mixture has to stay at rounding
+    level against the 50-digit evaluation."""
+    import mpmath as mp
+    v, f = O.load_mesh("llp")
+    m = O.Mesh(v, f)
+    rng = np.random.default_rng(3)
+    pts = []
+    for h in (3.0, 30.0, 120.0, 300.0, 600.0):
+        i = int(rng.integers(len(f)))
+        a, b, c = v[f[i, 0]], v[f[i, 1]], v[f[i, 2]]
+        n = np.cross(b - a, c - a)
+        pts.append((a + b + c) / 3 + h * n / np.linalg.norm(n) + rng.normal(size=3))
+    pts = np.array(pts)
+    acc = O.gravity(m, pts)
+    for i in range(len(pts)):
+        truth = _mp_gravity(v, f, pts[i], mp.mpf(G_CONST) * 533)
+        assert np.linalg.norm(acc[i] - truth) / np.linalg.norm(truth) < 5e-14
+
+
 @pytest.mark.parametrize("name,n,noise", [("lllp", 4000, 1e-11), ("llp", 4000, 5e-11), ("lp", 2000, 1e-10),
                                           ("full", 300, 5e-10)])
 def test_gravity_closed_forms_equal_literal_tsoulis(name, n, noise):

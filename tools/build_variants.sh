@@ -1,15 +1,24 @@
 #!/bin/bash
-# developer experiment: build stepper variants into gpurun_out-independent .so files under build/variants
+# developer experiment: build stepper variants into .so files under build/variants (tools/variant_bench.py times them)
 set -e
 cd "$(dirname "$0")/../toss_b200/csrc"
 mkdir -p ../../build/variants
 build() { # name flags...
   name=$1; shift
-  nvcc -O3 -std=c++17 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr "$@" -shared -o ../../build/variants/libtoss_$name.so api.cu gravity_kernels.cu stepper.cu fitness.cu -lcudart 2> ../../build/variants/$name.log
-  grep -A2 "stepper_kernelILb1" ../../build/variants/$name.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name"
+  nvcc -O3 -std=c++17 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr "$@" -shared -o ../../build/variants/libtoss_$name.so api.cu pairs.cu gravity_kernels.cu stepper.cu fitness.cu -lcudart 2> ../../build/variants/$name.log
+  grep -A2 "stepper_kernelILb1ELi1ELb0" ../../build/variants/$name.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name"
 }
-build base
-build u1 -DK2_UNROLL=1
-build w16u1 -DK2_WARPS=16 -DK2_MINBLOCKS=1 -DK2_STAGES=4 -DK2_UNROLL=1
-build w16 -DK2_WARPS=16 -DK2_MINBLOCKS=1 -DK2_STAGES=4
-build st2 -DK2_STAGES=2
+for v in "$@"; do
+  case $v in
+    base)   build base ;;
+    st4)    build st4 -DK2_STAGES=4 ;;
+    t64s6)  build t64s6 -DPAIR_TILE=64 -DK2_STAGES=6 ;;
+    t64s8)  build t64s8 -DPAIR_TILE=64 -DK2_STAGES=8 ;;
+    w20)    build w20 -DK2_WARPS=20 ;;
+    w24)    build w24 -DK2_WARPS=24 ;;
+    hint)   build hint -DK2_WAIT_HINT=20000 ;;
+    prof)   build prof -DK2_PROFILE ;;
+    prof4)  build prof4 -DK2_PROFILE -DK2_STAGES=4 ;;
+    *) echo "unknown variant $v"; exit 1 ;;
+  esac
+done

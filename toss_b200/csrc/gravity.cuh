@@ -11,12 +11,11 @@
 //     omega_p = 2 atan2(r0.(r1 x r2), l0 l1 l2 + l0 (r1.r2) + l1 (r2.r0) + l2 (r0.r1))
 // The unit of work is a PAIR of faces that share an edge (pairs.cu): LN of an edge depends only on its two end
 // points, |v - P| only on the vertex, so a pair needs 4 square roots and 5 edge terms where two single faces need
-// 6 and 6.  Work per pair-point on the common path (both faces seen under a small solid angle, edges under small
-// angles): 4 sqrt, ONE division shared by the seven quotients, five 7-coefficient atanh polynomials, two
-// 5-coefficient atan polynomials, ~110 other FP64 instructions -- everything on the FP64 pipe, nothing to feed
-// tensor cores.  A pair with a face close to the field point takes the general path (separate divisions, ln-based
-// atanh, full-range atan2).  Every operation is spelled out (tmath.cuh): the value is a fixed sequence of IEEE
-// operations.
+// 6 and 6.  Work per pair-point: 4 sqrt, ONE division shared by the seven quotients, five 7-coefficient atanh
+// polynomials, two 5-coefficient atan polynomials, ~110 other FP64 instructions -- everything on the FP64 pipe,
+// nothing to feed tensor cores.  A term whose argument is outside its polynomial's range (an edge or a face within a
+// few hundred metres of the field point) falls back ON ITS OWN to a separate division + ln-based atanh, or to the
+// full-range atan2.  Every operation is spelled out (tmath.cuh): the value is a fixed sequence of IEEE operations.
 #pragma once
 #include "common.cuh"
 #include "tmath.cuh"
@@ -24,9 +23,11 @@
 // Two faces that share an edge, one field point (pair record of common.cuh): S_A and S_B, the scalars that
 // multiply N_A and N_B.  Shared between the two: the distances to v0 and v1, r0.r1, l0*l1 and the edge term
 // LN_0 of e0; on the common path ONE division serves the five edge quotients and the two solid-angle quotients.
-template <class Fld>
+// kCompact: `scratch` is 96 doubles of shared memory owned by the calling warp, the whole warp is converged on the
+// call, and the out-of-range edge terms of the 32 pairs are compacted across the lanes (below).
+template <bool kCompact = false, class Fld>
 __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz, double &SA, double &SB,
-                                       double &hpA_out, double &hpB_out)
+                                       double &hpA_out, double &hpB_out, double *scratch = nullptr)
 {
     const double r0x = fld(0) - Px, r0y = fld(1) - Py, r0z = fld(2) - Pz;
     const double r1x = fld(3) - Px, r1y = fld(4) - Py, r1z = fld(5) - Pz;
@@ -55,38 +56,88 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
     const double denB = fma(l3, d01, fma(l0, d31, fma(l1, d03, l01 * l3)));
     const double numA = hpA * fld(41), numB = hpB * fld(42);
     const double G0 = fld(36), G1 = fld(37), G2 = fld(38), G3 = fld(39), G4 = fld(40);
-    double ln0, ln1, ln2, ln3, ln4, omA, omB;
-    bool fast = (denA > 0.0) && (denB > 0.0) && (fabs(numA) <= 0.1 * denA) && (fabs(numB) <= 0.1 * denB);
-    if (fast) {
-        const double P01 = a0 * a1, P2A = a2 * denA, P34 = a3 * a4;
-        const double X = P01 * P2A, Y = P34 * denB;
-        const double inv = tm_div(1.0, X * Y);
-        const double iX = Y * inv, iY = X * inv;
-        const double i01 = P2A * iX, i2A = P01 * iX, i34 = denB * iY, iB = P34 * iY;
-        const double z0 = (G0 * a1) * i01, z1 = (G1 * a0) * i01, z2 = (G2 * denA) * i2A;
-        const double qA = (numA * a2) * i2A;
-        const double z3 = (G3 * a4) * i34, z4 = (G4 * a3) * i34;
-        const double qB = numB * iB;
-        const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
-        fast = (z0s < 0.04) && (z1s < 0.04) && (z2s < 0.04) && (z3s < 0.04) && (z4s < 0.04);
-        if (fast) {
-            ln0 = tm_two_atanh_mm(z0, z0s);
-            ln1 = tm_two_atanh_mm(z1, z1s);
-            ln2 = tm_two_atanh_mm(z2, z2s);
-            ln3 = tm_two_atanh_mm(z3, z3s);
-            ln4 = tm_two_atanh_mm(z4, z4s);
-            omA = tm_two_atan_mm(qA, qA * qA);
-            omB = tm_two_atan_mm(qB, qB * qB);
+    // One division serves the five edge quotients and the two solid-angle quotients.  A face seen under a large
+    // solid angle (or from behind) leaves the shared product (its denominator is replaced by 1) and takes the
+    // full-range atan2; an edge seen under a large angle takes a division of its own and the ln-based atanh.  Each
+    // term chooses for itself (same rule in oracle/toss_oracle.c pair_term).
+    const bool okA = (denA > 0.0) && (fabs(numA) <= 0.1 * denA);
+    const bool okB = (denB > 0.0) && (fabs(numB) <= 0.1 * denB);
+    const double dA = okA ? denA : 1.0, dB = okB ? denB : 1.0;
+    const double P01 = a0 * a1, P2A = a2 * dA, P34 = a3 * a4;
+    const double X = P01 * P2A, Y = P34 * dB;
+    const double inv = tm_div(1.0, X * Y);
+    const double iX = Y * inv, iY = X * inv;
+    const double i01 = P2A * iX, i2A = P01 * iX, i34 = dB * iY, iB = P34 * iY;
+    const double z0 = (G0 * a1) * i01, z1 = (G1 * a0) * i01, z2 = (G2 * dA) * i2A;
+    const double qA = (numA * a2) * i2A;
+    const double z3 = (G3 * a4) * i34, z4 = (G4 * a3) * i34;
+    const double qB = numB * iB;
+    const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
+    double ln0 = tm_two_atanh_mm(z0, z0s);
+    double ln1 = tm_two_atanh_mm(z1, z1s);
+    double ln2 = tm_two_atanh_mm(z2, z2s);
+    double ln3 = tm_two_atanh_mm(z3, z3s);
+    double ln4 = tm_two_atanh_mm(z4, z4s);
+    double omA = tm_two_atan_mm(qA, qA * qA);
+    double omB = tm_two_atan_mm(qB, qB * qB);
+    // Out-of-range terms (rare: a pair within a few hundred metres of the field point; ~1.4 % of the 32-pair rows of
+    // an init-like population have any, then ~13 edge terms spread over ~5 lanes).  In the stepper every instruction
+    // spent here is paid by all the warps that share the tile ring, so the warp COMPACTS the bad edge terms of a row:
+    // the owners post (|G|, l1 + l2) to the warp's scratch, lane s evaluates term s, the owners read the values back
+    // -- ceil(#terms / 32) general evaluations per row instead of max-over-lanes(#terms of a lane).  Same operations
+    // on the same operands: the values do not depend on who computes them.
+    unsigned bad = (z0s < 0.04 ? 0u : 1u) | (z1s < 0.04 ? 0u : 2u) | (z2s < 0.04 ? 0u : 4u) | (z3s < 0.04 ? 0u : 8u) |
+                   (z4s < 0.04 ? 0u : 16u);
+    if (kCompact) {
+        constexpr unsigned kFull = 0xffffffffu;
+        if (__any_sync(kFull, bad != 0u)) {
+            const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+            const unsigned b0 = __ballot_sync(kFull, bad & 1u), b1 = __ballot_sync(kFull, bad & 2u),
+                           b2 = __ballot_sync(kFull, bad & 4u), b3 = __ballot_sync(kFull, bad & 8u),
+                           b4 = __ballot_sync(kFull, bad & 16u);
+            const unsigned c1 = __popc(b0), c2 = c1 + __popc(b1), c3 = c2 + __popc(b2), c4 = c3 + __popc(b3),
+                           total = c4 + __popc(b4);
+            const unsigned p0 = __popc(b0 & lt), p1 = c1 + __popc(b1 & lt), p2 = c2 + __popc(b2 & lt),
+                           p3 = c3 + __popc(b3 & lt), p4 = c4 + __popc(b4 & lt);
+            double *sG = scratch, *sa = scratch + 32, *sv = scratch + 64;
+            for (unsigned base = 0; base < total; base += 32u) {
+                if ((bad & 1u) && p0 - base < 32u) { sG[p0 - base] = G0; sa[p0 - base] = a0; }
+                if ((bad & 2u) && p1 - base < 32u) { sG[p1 - base] = G1; sa[p1 - base] = a1; }
+                if ((bad & 4u) && p2 - base < 32u) { sG[p2 - base] = G2; sa[p2 - base] = a2; }
+                if ((bad & 8u) && p3 - base < 32u) { sG[p3 - base] = G3; sa[p3 - base] = a3; }
+                if ((bad & 16u) && p4 - base < 32u) { sG[p4 - base] = G4; sa[p4 - base] = a4; }
+                __syncwarp();
+                if (base + lane < total) sv[lane] = tm_two_atanh(tm_div(sG[lane], sa[lane]));
+                __syncwarp();
+                if ((bad & 1u) && p0 - base < 32u) ln0 = sv[p0 - base];
+                if ((bad & 2u) && p1 - base < 32u) ln1 = sv[p1 - base];
+                if ((bad & 4u) && p2 - base < 32u) ln2 = sv[p2 - base];
+                if ((bad & 8u) && p3 - base < 32u) ln3 = sv[p3 - base];
+                if ((bad & 16u) && p4 - base < 32u) ln4 = sv[p4 - base];
+                __syncwarp();
+            }
         }
+        bad = 0u;
     }
-    if (!fast) {   // a face close to the field point: separate divisions, ln-based atanh, full-range atan2
-        ln0 = tm_two_atanh(tm_div(G0, a0));
-        ln1 = tm_two_atanh(tm_div(G1, a1));
-        ln2 = tm_two_atanh(tm_div(G2, a2));
-        ln3 = tm_two_atanh(tm_div(G3, a3));
-        ln4 = tm_two_atanh(tm_div(G4, a4));
-        omA = 2.0 * tm_atan2(numA, denA);
-        omB = 2.0 * tm_atan2(numB, denB);
+    while (bad) {
+        const unsigned k = __ffs(bad) - 1;
+        bad &= bad - 1;
+        const double Gk = k == 0 ? G0 : k == 1 ? G1 : k == 2 ? G2 : k == 3 ? G3 : G4;
+        const double ak = k == 0 ? a0 : k == 1 ? a1 : k == 2 ? a2 : k == 3 ? a3 : a4;
+        const double v = tm_two_atanh(tm_div(Gk, ak));
+        if (k == 0) ln0 = v;
+        else if (k == 1) ln1 = v;
+        else if (k == 2) ln2 = v;
+        else if (k == 3) ln3 = v;
+        else ln4 = v;
+    }
+    unsigned badw = (okA ? 0u : 1u) | (okB ? 0u : 2u);
+    while (badw) {
+        const bool isA = badw & 1u;
+        badw &= badw - 1;
+        const double v = 2.0 * tm_atan2(isA ? numA : numB, isA ? denA : denB);
+        if (isA) omA = v;
+        else omB = v;
     }
     hpA_out = hpA;
     hpB_out = hpB;
@@ -95,12 +146,12 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
 }
 
 // acc += N_A S_A + N_B S_B (and pot += hp_A S_A + hp_B S_B)
-template <bool kPot, class Fld>
+template <bool kPot, bool kCompact = false, class Fld>
 __device__ __forceinline__ void pair_term(Fld fld, double Px, double Py, double Pz, double &ax, double &ay,
-                                          double &az, double &pot)
+                                          double &az, double &pot, double *scratch = nullptr)
 {
     double SA, SB, hpA, hpB;
-    pair_S(fld, Px, Py, Pz, SA, SB, hpA, hpB);
+    pair_S<kCompact>(fld, Px, Py, Pz, SA, SB, hpA, hpB, scratch);
     ax = fma(fld(15), SB, fma(fld(12), SA, ax));
     ay = fma(fld(16), SB, fma(fld(13), SA, ay));
     az = fma(fld(17), SB, fma(fld(14), SA, az));
@@ -163,12 +214,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "WAIT_LOOP:\n"
+#ifdef K2_WAIT_HINT
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+#endif
         "@p bra WAIT_DONE;\n"
         "bra WAIT_LOOP;\n"
         "WAIT_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
+#ifdef K2_WAIT_HINT
+        , "r"((uint32_t)K2_WAIT_HINT)
+#endif
         : "memory");
 }
 __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar)

@@ -95,6 +95,7 @@ __device__ __forceinline__ void refill_if_released(uint64_t *bars, int *claim, d
 // shared buffer; after a team barrier the owner adds N_A S_A + N_B S_B in the canonical order (row 0, 1, 2, ... of every tile).  The
 // arithmetic, and therefore every result bit, is the same for any team size.
 enum : int { kModeGrav = 0, kModeSkip = 1, kModeRetire = 2 };
+constexpr int kScratchDoubles = 96;             // pair_S scratch per warp: |G|[32] | l1+l2[32] | value[32]
 constexpr int kTeamBufDoubles = 4 + 2 * 4 * 64;   // P[3] + mode | S[2 buffers][4 rows][S_A x 32 lanes | S_B x 32 lanes]
 
 __device__ __forceinline__ void team_bar(int team, int nthreads)
@@ -117,6 +118,9 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     double *sy = wstate, *sk = wstate + 6, *meta = wstate + 84, *seg_t = wstate + 86, *sdv = seg_t + (a.n_man + 2);
     double *tbuf = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)kK2Warps * warp_state_doubles(a.n_man) +
                    (size_t)team * kTeamBufDoubles;                       // team mailbox: P, mode, S buffers
+    // per-warp scratch of pair_S (compaction of the out-of-range edge terms of a row): 96 doubles
+    double *scr = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)kK2Warps * warp_state_doubles(a.n_man) +
+                  (size_t)(kK2Warps / 2) * kTeamBufDoubles + (size_t)wid * kScratchDoubles;
     volatile double *tP = tbuf;
     volatile int *tmode = reinterpret_cast<volatile int *>(tbuf + 3);
     double *sbuf = tbuf + 4;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                         for (int r = rank; r < rows; r += kTeam) {
                             const double *col = tile + 32 * r;
                             double SA, SB, hpA, hpB;
-                            pair_S([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, SA, SB, hpA, hpB);
+                            pair_S<true>([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, SA, SB, hpA, hpB, scr);
                             sbuf[(spar * 4 + r) * 64 + lane] = SA;
                             sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                         }
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     for (int r = rank; r < rows; r += kTeam) {
                         const double *col = mesh + 32 * (4 * v + r) + lane;
                         double SA, SB, hpA, hpB;
-                        pair_S([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, SA, SB, hpA, hpB);
+                        pair_S<true>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, SA, SB, hpA, hpB, scr);
                         sbuf[(spar * 4 + r) * 64 + lane] = SA;
                         sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                     }
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     for (int r = 0; r < rows; r += kTeam) {
                         const double *col = tile + 32 * r;
                         double SA, SB, hpA, hpB;
-                        pair_S([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, SA, SB, hpA, hpB);
+                        pair_S<true>([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, SA, SB, hpA, hpB, scr);
                         sbuf[(spar * 4 + r) * 64 + lane] = SA;
                         sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                     }
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 #pragma unroll kK2Unroll
                     for (int f = 0; f < f_end; f += 32) {
                         const double *col = tile + f;
-                        pair_term<false>([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, ax, ay, az, pv);
+                        pair_term<false, true>([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, ax, ay, az, pv, scr);
                     }
                 }
                 __syncwarp();
@@ -482,7 +486,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     for (int r = 0; r < rows; r += kTeam) {
                         const double *col = mesh + 32 * (4 * v + r) + lane;
                         double SA, SB, hpA, hpB;
-                        pair_S([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, SA, SB, hpA, hpB);
+                        pair_S<true>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, SA, SB, hpA, hpB, scr);
                         sbuf[(spar * 4 + r) * 64 + lane] = SA;
                         sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                     }
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 #pragma unroll kK2Unroll
                 for (int f = lane; f < Fp; f += 32) {
                     const double *col = mesh + f;
-                    pair_term<false>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, ax, ay, az, pv);
+                    pair_term<false, true>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, ax, ay, az, pv, scr);
                 }
             }
         }
@@ -787,7 +791,8 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
         px.proxy_soft2 = ctx->mascon_soft2;
         px.proxy_cost = cost;
         const size_t psmem = (size_t)4 * ctx->n_mascons * 8 + (size_t)kK2Warps * warp_state_doubles(n_man) * 8 +
-                             kK2BarSlots * 8 + (size_t)(kK2Warps / 2) * kTeamBufDoubles * 8;
+                             kK2BarSlots * 8 + (size_t)(kK2Warps / 2) * kTeamBufDoubles * 8 +
+                             (size_t)kK2Warps * kScratchDoubles * 8;
         int pctas = (pop + kK2Warps - 1) / kK2Warps;
         if (pctas > K2_MINBLOCKS * ctx->sm_count) pctas = K2_MINBLOCKS * ctx->sm_count;
         TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -800,7 +805,7 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     }
 
     const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 +
-                               (size_t)(kK2Warps / 2) * kTeamBufDoubles * 8;
+                               (size_t)(kK2Warps / 2) * kTeamBufDoubles * 8 + (size_t)kK2Warps * kScratchDoubles * 8;
     const size_t resident_bytes = (size_t)kPairFields * ctx->Ppad32 * 8 + state_bytes;
     const size_t stream_bytes = (size_t)kK2Stages * kPairTileBytes + state_bytes;
     const bool resident = resident_bytes <= (size_t)(200 / K2_MINBLOCKS) * 1024;   // every CTA on an SM keeps its own copy
