@@ -354,6 +354,14 @@ static void gravity_point_direct(const orc_mesh *m, const double P[3], double ac
  * The seven quotients share ONE division and atanh / atan are short odd minimax polynomials; a term whose
  * argument is out of the polynomial's range (an edge or a face close to the field point) falls back, on its own,
  * to a division of its own + ln-based atanh, or to the full-range atan2. */
+#define ORC_HI_Z2MAX 0x3FA47AE1
+#define ORC_HI_Q2MAX 0x3F847AE1
+static inline int32_t orc_hi(double x)   /* high word of the IEEE-754 pattern, as a signed integer */
+{
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    return (int32_t)(b >> 32);
+}
 static inline void pair_term(const double *rc, const double P[3], double *ax, double *ay, double *az, double *pv)
 {
     const double r0x = rc[0] - P[0], r0y = rc[1] - P[1], r0z = rc[2] - P[2];
@@ -383,30 +391,35 @@ static inline void pair_term(const double *rc, const double P[3], double *ax, do
     const double denA = ORC_FMA(l2, d01, ORC_FMA(l1, d20, ORC_FMA(l0, d12, l01 * l2)));
     const double denB = ORC_FMA(l3, d01, ORC_FMA(l0, d31, ORC_FMA(l1, d03, l01 * l3)));
     const double numA = hpA * rc[41], numB = hpB * rc[42];
-    /* One division serves the five edge quotients and the two solid-angle quotients; a face seen under a large
-     * solid angle (or from behind) leaves the shared product (its denominator is replaced by 1) and takes the
-     * full-range atan2, an edge seen under a large angle takes a division of its own and the ln-based atanh.
-     * Each term chooses for itself, so a close face costs only the terms that need it. */
-    const int okA = (denA > 0.0) && (fabs(numA) <= 0.1 * denA);
-    const int okB = (denB > 0.0) && (fabs(numB) <= 0.1 * denB);
-    const double dA = okA ? denA : 1.0, dB = okB ? denB : 1.0;
-    const double P01 = a0 * a1, P2A = a2 * dA, P34 = a3 * a4;
-    const double X = P01 * P2A, Y = P34 * dB;
+    /* One division serves the five edge quotients and the two solid-angle quotients (X Y is a product of lengths
+     * and of the two solid-angle denominators: it only has to be non-zero; were a denominator exactly 0 every
+     * quotient would come out non-finite, fail its range test and take its own way).  An edge seen under a large
+     * angle takes a division of its own and the ln-based atanh, a face seen under a large solid angle (or from
+     * behind) the full-range atan2.  Each term chooses for itself, so a close face costs only the terms that need
+     * it. */
+    const double P01 = a0 * a1, P2A = a2 * denA, P34 = a3 * a4;
+    const double X = P01 * P2A, Y = P34 * denB;
     const double inv = 1.0 / (X * Y);
     const double iX = Y * inv, iY = X * inv;
-    const double i01 = P2A * iX, i2A = P01 * iX, i34 = dB * iY, iB = P34 * iY;
-    const double z0 = (G[0] * a1) * i01, z1 = (G[1] * a0) * i01, z2 = (G[2] * dA) * i2A;
+    const double i01 = P2A * iX, i2A = P01 * iX, i34 = denB * iY, iB = P34 * iY;
+    const double z0 = (G[0] * a1) * i01, z1 = (G[1] * a0) * i01, z2 = (G[2] * denA) * i2A;
     const double qA = (numA * a2) * i2A;
     const double z3 = (G[3] * a4) * i34, z4 = (G[4] * a3) * i34;
     const double qB = numB * iB;
+    /* Range tests: the thresholds are doubles whose low word is 0 (0x3FA47AE1'00000000 = 0.04 - 9e-10 for z^2,
+     * 0x3F847AE1'00000000 = 0.01 - 2e-10 for q^2), so for x >= 0 `x < threshold` is a comparison of the high words
+     * (the CUDA side does it on the integer pipe); a NaN fails it; `den > 0` likewise reads hi(den) > 0. */
     const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
-    const double ln0 = (z0s < 0.04) ? orc_two_atanh_mm(z0, z0s) : orc_two_atanh(G[0] / a0);
-    const double ln1 = (z1s < 0.04) ? orc_two_atanh_mm(z1, z1s) : orc_two_atanh(G[1] / a1);
-    const double ln2 = (z2s < 0.04) ? orc_two_atanh_mm(z2, z2s) : orc_two_atanh(G[2] / a2);
-    const double ln3 = (z3s < 0.04) ? orc_two_atanh_mm(z3, z3s) : orc_two_atanh(G[3] / a3);
-    const double ln4 = (z4s < 0.04) ? orc_two_atanh_mm(z4, z4s) : orc_two_atanh(G[4] / a4);
-    const double omA = okA ? orc_two_atan_mm(qA, qA * qA) : 2.0 * orc_atan2(numA, denA);
-    const double omB = okB ? orc_two_atan_mm(qB, qB * qB) : 2.0 * orc_atan2(numB, denB);
+    const double qAs = qA * qA, qBs = qB * qB;
+    const int okA = (orc_hi(denA) > 0) && (orc_hi(qAs) < ORC_HI_Q2MAX);
+    const int okB = (orc_hi(denB) > 0) && (orc_hi(qBs) < ORC_HI_Q2MAX);
+    const double ln0 = (orc_hi(z0s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z0, z0s) : orc_two_atanh(G[0] / a0);
+    const double ln1 = (orc_hi(z1s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z1, z1s) : orc_two_atanh(G[1] / a1);
+    const double ln2 = (orc_hi(z2s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z2, z2s) : orc_two_atanh(G[2] / a2);
+    const double ln3 = (orc_hi(z3s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z3, z3s) : orc_two_atanh(G[3] / a3);
+    const double ln4 = (orc_hi(z4s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z4, z4s) : orc_two_atanh(G[4] / a4);
+    const double omA = okA ? orc_two_atan_mm(qA, qAs) : 2.0 * orc_atan2(numA, denA);
+    const double omB = okB ? orc_two_atan_mm(qB, qBs) : 2.0 * orc_atan2(numB, denB);
     const double SA = ORC_FMA(-hpA, omA, ORC_FMA(hA2, ln2, ORC_FMA(hA1, ln1, hA0 * ln0)));
     const double SB = ORC_FMA(-hpB, omB, ORC_FMA(hB2, ln4, ORC_FMA(hB1, ln3, hB0 * ln0)));
     *ax = ORC_FMA(NB[0], SB, ORC_FMA(NA[0], SA, *ax));

@@ -17,6 +17,7 @@ for v in "$@"; do
     w20)    build w20 -DK2_WARPS=20 ;;
     w24)    build w24 -DK2_WARPS=24 ;;
     hint)   build hint -DK2_WAIT_HINT=20000 ;;
+    nocompact) build nocompact -DK2_NO_COMPACT ;;
     prof)   build prof -DK2_PROFILE ;;
     prof4)  build prof4 -DK2_PROFILE -DK2_STAGES=4 ;;
     *) echo "unknown variant $v"; exit 1 ;;

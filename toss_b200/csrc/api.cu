@@ -188,21 +188,23 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
     // (1) AoS, 44 doubles per pair, padded to whole 32-pair tiles          -> K1a thread-per-point
     std::vector<double> aos((size_t)ctx->n_pair_aos_tiles * kPairAosTile * kPairAosStride, 0.0);
     for (int i = 0; i < ctx->n_pair_aos_tiles * kPairAosTile; ++i) pair_or_pad(i, &aos[(size_t)i * kPairAosStride]);
-    // (2) flat SoA [43][Ppad32]                                           -> resident stepper, K1b
-    std::vector<double> soa((size_t)kPairFields * ctx->Ppad32);
+    // (2) flat slot table [22][Ppad32] double2 (slot j = fields 2j, 2j+1)  -> resident stepper, K1b
+    std::vector<double> soa((size_t)2 * kPairSlots * ctx->Ppad32, 0.0);
     for (int i = 0; i < ctx->Ppad32; ++i) {
         double tmp[kPairFields];
         pair_or_pad(i, tmp);
-        for (int k = 0; k < kPairFields; ++k) soa[(size_t)k * ctx->Ppad32 + i] = tmp[k];
+        for (int k = 0; k < kPairFields; ++k) soa[((size_t)(k >> 1) * ctx->Ppad32 + i) * 2 + (k & 1)] = tmp[k];
     }
-    // (3) tiled SoA [n_tiles][43][128] -> streaming stepper.  Pair i sits in tile i/128, slot i%128, so lane l
-    //     still owns pairs l, l+32, l+64, ... in increasing order: the same summation order as the flat layout.
-    std::vector<double> tiles((size_t)ctx->n_pair_tiles * kPairTileDoubles);
+    // (3) tiled slot table [n_tiles][22][128] double2 -> streaming stepper.  Pair i sits in tile i/128, slot row
+    //     position i%128, so lane l still owns pairs l, l+32, l+64, ... in increasing order: the same summation
+    //     order as the flat layout.
+    std::vector<double> tiles((size_t)ctx->n_pair_tiles * kPairTileDoubles, 0.0);
     for (int t = 0; t < ctx->n_pair_tiles; ++t)
         for (int j = 0; j < kPairTile; ++j) {
             double tmp[kPairFields];
             pair_or_pad(t * kPairTile + j, tmp);
-            for (int k = 0; k < kPairFields; ++k) tiles[((size_t)t * kPairFields + k) * kPairTile + j] = tmp[k];
+            for (int k = 0; k < kPairFields; ++k)
+                tiles[(((size_t)t * kPairSlots + (k >> 1)) * kPairTile + j) * 2 + (k & 1)] = tmp[k];
         }
     // (4) the faces themselves, original vertex order, [9][Fpad32]        -> ray casting (K5, event points)
     std::vector<double> ray((size_t)kRayFields * ctx->Fpad32);

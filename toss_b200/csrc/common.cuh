@@ -29,8 +29,25 @@ constexpr int kPairAosTile = 32;        // K1 (thread-per-point) TMA tile: 32 pa
 #ifndef PAIR_TILE
 #define PAIR_TILE 128
 #endif
-constexpr int kPairTile = PAIR_TILE;    // K2 (lane-per-pair) TMA tile: 43 x 128 x 8 B = 44 032 B, 4 rows of 32 pairs
-constexpr int kPairTileDoubles = kPairFields * kPairTile;
+constexpr int kPairTile = PAIR_TILE;    // K2 (lane-per-pair) TMA tile: 22 x 128 x 16 B = 45 056 B, 4 rows of 32 pairs
+// Lane-per-pair tables store the 43 fields as 22 double2 SLOTS (slot j = fields 2j, 2j+1; the 44th double is 0):
+// [22][n] double2, so a lane fetches two fields with one 16-byte load (LDS.128 / LDG.128, conflict-free: consecutive
+// lanes read consecutive 16-byte words) -- 22 load instructions per pair instead of 43.
+constexpr int kPairSlots = 22;
+constexpr int kPairTileDoubles = 2 * kPairSlots * kPairTile;
+
+// field accessor of a slot table: col points at this lane's double2 of slot 0, `stride` = pairs per slot row
+template <bool kLdg>
+struct PairCols {
+    const double2 *col;
+    int stride;
+    __device__ __forceinline__ double operator()(int k) const
+    {
+        const double2 *p = col + (size_t)(k >> 1) * stride;
+        const double2 v = kLdg ? __ldg(p) : *p;
+        return (k & 1) ? v.y : v.x;
+    }
+};
 constexpr int kRayFields = 9;
 constexpr double kPadVertex = 1.0e9;    // padding faces sit here with N = n = |G| = 2A = 0 -> contribute exactly 0
 constexpr double kGravConst = 6.67430e-11;   // CODATA-2018, as polyhedral_gravity >= 2
@@ -52,8 +69,8 @@ struct toss_ctx {
     int n_pair_aos_tiles = 0;        // ceil(n_pairs / 32)
     int n_pair_tiles = 0;            // ceil(n_pairs / 128)
     double *d_pair_aos = nullptr;    // [n_pair_aos_tiles*32][44]      K1a
-    double *d_pair_soa = nullptr;    // [43][Ppad32]                   K1b, resident stepper
-    double *d_pair_tiles = nullptr;  // [n_pair_tiles][43][128]        streaming stepper
+    double *d_pair_soa = nullptr;    // [22][Ppad32] double2 slots      K1b, resident stepper
+    double *d_pair_tiles = nullptr;  // [n_pair_tiles][22][128] double2 streaming stepper
     double *d_ray_soa = nullptr;     // [9][Fpad32] v0 v1 v2 of every face in mesh order: ray casting
     int32_t *h_pairs = nullptr;      // [n_pairs][3] fA, qA, fB: the pairing (toss_mesh_pairs)
     // voxel grid

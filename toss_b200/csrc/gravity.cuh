@@ -56,41 +56,56 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
     const double denB = fma(l3, d01, fma(l0, d31, fma(l1, d03, l01 * l3)));
     const double numA = hpA * fld(41), numB = hpB * fld(42);
     const double G0 = fld(36), G1 = fld(37), G2 = fld(38), G3 = fld(39), G4 = fld(40);
-    // One division serves the five edge quotients and the two solid-angle quotients.  A face seen under a large
-    // solid angle (or from behind) leaves the shared product (its denominator is replaced by 1) and takes the
-    // full-range atan2; an edge seen under a large angle takes a division of its own and the ln-based atanh.  Each
-    // term chooses for itself (same rule in oracle/toss_oracle.c pair_term).
-    const bool okA = (denA > 0.0) && (fabs(numA) <= 0.1 * denA);
-    const bool okB = (denB > 0.0) && (fabs(numB) <= 0.1 * denB);
-    const double dA = okA ? denA : 1.0, dB = okB ? denB : 1.0;
-    const double P01 = a0 * a1, P2A = a2 * dA, P34 = a3 * a4;
-    const double X = P01 * P2A, Y = P34 * dB;
+    // One division serves the five edge quotients and the two solid-angle quotients (X Y is a product of lengths and
+    // of the two solid-angle denominators: it only has to be non-zero; were a denominator exactly 0 every quotient
+    // would come out non-finite and every term would take its own way below).
+    const double P01 = a0 * a1, P2A = a2 * denA, P34 = a3 * a4;
+    const double X = P01 * P2A, Y = P34 * denB;
     const double inv = tm_div(1.0, X * Y);
     const double iX = Y * inv, iY = X * inv;
-    const double i01 = P2A * iX, i2A = P01 * iX, i34 = dB * iY, iB = P34 * iY;
-    const double z0 = (G0 * a1) * i01, z1 = (G1 * a0) * i01, z2 = (G2 * dA) * i2A;
+    const double i01 = P2A * iX, i2A = P01 * iX, i34 = denB * iY, iB = P34 * iY;
+    const double z0 = (G0 * a1) * i01, z1 = (G1 * a0) * i01, z2 = (G2 * denA) * i2A;
     const double qA = (numA * a2) * i2A;
     const double z3 = (G3 * a4) * i34, z4 = (G4 * a3) * i34;
     const double qB = numB * iB;
     const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
-    double ln0 = tm_two_atanh_mm(z0, z0s);
-    double ln1 = tm_two_atanh_mm(z1, z1s);
-    double ln2 = tm_two_atanh_mm(z2, z2s);
-    double ln3 = tm_two_atanh_mm(z3, z3s);
-    double ln4 = tm_two_atanh_mm(z4, z4s);
-    double omA = tm_two_atan_mm(qA, qA * qA);
-    double omB = tm_two_atan_mm(qB, qB * qB);
-    // Out-of-range terms (rare: a pair within a few hundred metres of the field point; ~1.4 % of the 32-pair rows of
-    // an init-like population have any, then ~13 edge terms spread over ~5 lanes).  In the stepper every instruction
-    // spent here is paid by all the warps that share the tile ring, so the warp COMPACTS the bad edge terms of a row:
-    // the owners post (|G|, l1 + l2) to the warp's scratch, lane s evaluates term s, the owners read the values back
-    // -- ceil(#terms / 32) general evaluations per row instead of max-over-lanes(#terms of a lane).  Same operations
-    // on the same operands: the values do not depend on who computes them.
-    unsigned bad = (z0s < 0.04 ? 0u : 1u) | (z1s < 0.04 ? 0u : 2u) | (z2s < 0.04 ? 0u : 4u) | (z3s < 0.04 ? 0u : 8u) |
-                   (z4s < 0.04 ? 0u : 16u);
+    const double qAs = qA * qA, qBs = qB * qB;
+    // HALF values from here on: atanh(z) and atan(q) instead of 2 atanh(z) = LN and 2 atan(q) = omega.  Scaling by
+    // 2 is exact, so S/2 and the accumulated sum/2 carry the same bits; the callers multiply by 2 G rho at the end.
+    double ln0 = tm_atanh_mm(z0, z0s);
+    double ln1 = tm_atanh_mm(z1, z1s);
+    double ln2 = tm_atanh_mm(z2, z2s);
+    double ln3 = tm_atanh_mm(z3, z3s);
+    double ln4 = tm_atanh_mm(z4, z4s);
+    double omA = tm_atan_mm(qA, qAs);
+    double omB = tm_atan_mm(qB, qBs);
+    // Range tests.  An edge seen under a large angle (z^2 >= kZ2Max) takes a division of its own and the ln-based
+    // atanh; a face seen under a large solid angle or from behind (den <= 0 or q^2 >= kQ2Max) the full-range atan2.
+    // Each term chooses for itself; the rule is part of the arithmetic specification.  The
+    // thresholds are doubles whose low word is 0, so `x < threshold` for x >= 0 is a comparison of the HIGH words
+    // alone (a NaN pattern is above every finite one): the whole test costs two 3-input integer maxima, one
+    // max, one min and three compares on the integer pipe instead of nine FP64-pipe compares -- the FP64 pipe (two
+    // issue slots per instruction) is what bounds this loop.
+    const int hz0 = __double2hiint(z0s), hz1 = __double2hiint(z1s), hz2 = __double2hiint(z2s),
+              hz3 = __double2hiint(z3s), hz4 = __double2hiint(z4s);
+    const int hqA = __double2hiint(qAs), hqB = __double2hiint(qBs), hdA = __double2hiint(denA),
+              hdB = __double2hiint(denB);
+    const bool anybad = (max(max(max(hz0, hz1), hz2), max(hz3, hz4)) >= kHiZ2Max) | (max(hqA, hqB) >= kHiQ2Max) |
+                        (min(hdA, hdB) <= 0);
+    unsigned bad = 0u, badw = 0u;
     if (kCompact) {
+        // Out-of-range terms are rare (a pair within a few hundred metres of the field point; ~1.4 % of the 32-pair
+        // rows of an init-like population have any, then ~13 edge terms spread over ~5 lanes).  In the stepper every
+        // instruction spent here is paid by all the warps that share the tile ring, so the warp COMPACTS the bad
+        // edge terms of a row: the owners post (|G|, l1 + l2) to the warp's scratch, lane s evaluates term s, the
+        // owners read the values back -- ceil(#terms / 32) general evaluations per row instead of
+        // max-over-lanes(#terms of a lane).  Same operations on the same operands: the values do not depend on who
+        // computes them.
         constexpr unsigned kFull = 0xffffffffu;
-        if (__any_sync(kFull, bad != 0u)) {
+        if (__any_sync(kFull, anybad)) {
+            bad = (hz0 < kHiZ2Max ? 0u : 1u) | (hz1 < kHiZ2Max ? 0u : 2u) | (hz2 < kHiZ2Max ? 0u : 4u) |
+                  (hz3 < kHiZ2Max ? 0u : 8u) | (hz4 < kHiZ2Max ? 0u : 16u);
+            badw = ((hdA > 0 && hqA < kHiQ2Max) ? 0u : 1u) | ((hdB > 0 && hqB < kHiQ2Max) ? 0u : 2u);
             const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
             const unsigned b0 = __ballot_sync(kFull, bad & 1u), b1 = __ballot_sync(kFull, bad & 2u),
                            b2 = __ballot_sync(kFull, bad & 4u), b3 = __ballot_sync(kFull, bad & 8u),
@@ -107,7 +122,7 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
                 if ((bad & 8u) && p3 - base < 32u) { sG[p3 - base] = G3; sa[p3 - base] = a3; }
                 if ((bad & 16u) && p4 - base < 32u) { sG[p4 - base] = G4; sa[p4 - base] = a4; }
                 __syncwarp();
-                if (base + lane < total) sv[lane] = tm_two_atanh(tm_div(sG[lane], sa[lane]));
+                if (base + lane < total) sv[lane] = 0.5 * tm_two_atanh(tm_div(sG[lane], sa[lane]));
                 __syncwarp();
                 if ((bad & 1u) && p0 - base < 32u) ln0 = sv[p0 - base];
                 if ((bad & 2u) && p1 - base < 32u) ln1 = sv[p1 - base];
@@ -116,26 +131,29 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
                 if ((bad & 16u) && p4 - base < 32u) ln4 = sv[p4 - base];
                 __syncwarp();
             }
+            bad = 0u;
         }
-        bad = 0u;
+    } else if (anybad) {
+        bad = (hz0 < kHiZ2Max ? 0u : 1u) | (hz1 < kHiZ2Max ? 0u : 2u) | (hz2 < kHiZ2Max ? 0u : 4u) |
+              (hz3 < kHiZ2Max ? 0u : 8u) | (hz4 < kHiZ2Max ? 0u : 16u);
+        badw = ((hdA > 0 && hqA < kHiQ2Max) ? 0u : 1u) | ((hdB > 0 && hqB < kHiQ2Max) ? 0u : 2u);
     }
-    while (bad) {
+    while (bad) {   // per-lane walk through the bad edge terms (callers without a converged warp)
         const unsigned k = __ffs(bad) - 1;
         bad &= bad - 1;
         const double Gk = k == 0 ? G0 : k == 1 ? G1 : k == 2 ? G2 : k == 3 ? G3 : G4;
         const double ak = k == 0 ? a0 : k == 1 ? a1 : k == 2 ? a2 : k == 3 ? a3 : a4;
-        const double v = tm_two_atanh(tm_div(Gk, ak));
+        const double v = 0.5 * tm_two_atanh(tm_div(Gk, ak));
         if (k == 0) ln0 = v;
         else if (k == 1) ln1 = v;
         else if (k == 2) ln2 = v;
         else if (k == 3) ln3 = v;
         else ln4 = v;
     }
-    unsigned badw = (okA ? 0u : 1u) | (okB ? 0u : 2u);
     while (badw) {
         const bool isA = badw & 1u;
         badw &= badw - 1;
-        const double v = 2.0 * tm_atan2(isA ? numA : numB, isA ? denA : denB);
+        const double v = tm_atan2(isA ? numA : numB, isA ? denA : denB);
         if (isA) omA = v;
         else omB = v;
     }
@@ -145,7 +163,7 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
     SB = fma(-hpB, omB, fma(hB2, ln4, fma(hB1, ln3, hB0 * ln0)));
 }
 
-// acc += N_A S_A + N_B S_B (and pot += hp_A S_A + hp_B S_B)
+// acc += (N_A S_A + N_B S_B) / 2 (and pot += (hp_A S_A + hp_B S_B) / 2): pair_S works in exact halves
 template <bool kPot, bool kCompact = false, class Fld>
 __device__ __forceinline__ void pair_term(Fld fld, double Px, double Py, double Pz, double &ax, double &ay,
                                           double &az, double &pot, double *scratch = nullptr)

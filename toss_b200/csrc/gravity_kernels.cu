@@ -72,16 +72,17 @@ gravity_points_kernel(const double *__restrict__ pair_aos, int n_tiles, int last
         if (lane == 0) mbar_arrive(&empty[s]);
     }
     if (i < n) {
-        acc[3 * i] = Grho * ax;
-        acc[3 * i + 1] = Grho * ay;
-        acc[3 * i + 2] = Grho * az;
-        if (kPot) pot[i] = 0.5 * Grho * pv;
+        const double G2 = Grho + Grho;   // pair_term accumulates exact halves
+        acc[3 * i] = G2 * ax;
+        acc[3 * i + 1] = G2 * ay;
+        acc[3 * i + 2] = G2 * az;
+        if (kPot) pot[i] = Grho * pv;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K1b  warp-per-point (few points: the single-point `evaluable(x)` call, compute_motion batches):
-// lanes stride the pair records of the flat SoA (coalesced 256 B loads), butterfly-shuffle reduction.
+// lanes stride the pair records of the flat slot table (coalesced 512 B loads), butterfly-shuffle reduction.
 // Same lane->face map and reduction tree as the stepper, so values are identical to the RHS it sees.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_gravity_global(const double *__restrict__ soa, int Ppad32, double Px, double Py,
@@ -90,8 +91,8 @@ __device__ __forceinline__ void warp_gravity_global(const double *__restrict__ s
 {
     ax = ay = az = pv = 0.0;
     for (int f = lane; f < Ppad32; f += 32) {
-        const double *col = soa + f;
-        pair_term<true>([col, Ppad32](int k) { return __ldg(col + (size_t)k * Ppad32); }, Px, Py, Pz, ax, ay, az, pv);
+        const PairCols<true> cols{reinterpret_cast<const double2 *>(soa) + f, Ppad32};
+        pair_term<true>(cols, Px, Py, Pz, ax, ay, az, pv);
     }
     ax = warp_sum(ax);
     ay = warp_sum(ay);
@@ -110,10 +111,11 @@ __global__ void __launch_bounds__(256) gravity_warp_kernel(const double *__restr
     double ax, ay, az, pv;
     warp_gravity_global(soa, Ppad32, pts[3 * w], pts[3 * w + 1], pts[3 * w + 2], lane, ax, ay, az, pv);
     if (lane == 0) {
-        acc[3 * w] = Grho * ax;
-        acc[3 * w + 1] = Grho * ay;
-        acc[3 * w + 2] = Grho * az;
-        if (pot) pot[w] = 0.5 * Grho * pv;
+        const double G2 = Grho + Grho;   // pair_term accumulates exact halves
+        acc[3 * w] = G2 * ax;
+        acc[3 * w + 1] = G2 * ay;
+        acc[3 * w + 2] = G2 * az;
+        if (pot) pot[w] = Grho * pv;
     }
 }
 
@@ -137,9 +139,10 @@ __global__ void __launch_bounds__(256) compute_motion_kernel(const double *__res
         o[0] = y[3];
         o[1] = y[4];
         o[2] = y[5];
-        o[3] = -(Grho * ax);
-        o[4] = -(Grho * ay);
-        o[5] = -(Grho * az);
+        const double G2 = Grho + Grho;   // pair_term accumulates exact halves
+        o[3] = -(G2 * ax);
+        o[4] = -(G2 * ay);
+        o[5] = -(G2 * az);
     }
 }
 

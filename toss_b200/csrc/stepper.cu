@@ -13,7 +13,7 @@
 // Two mesh-staging modes:
 //   RESIDENT  the flat SoA pair table fits in shared memory (lllp, llp): TMA-copied once per CTA;
 //             warps then run completely independently.
-//   STREAM    (lp, full) the table streams through a 3-stage ring of 44 KB SoA tiles (128 pairs) filled by TMA
+//   STREAM    (lp, full) the table streams through a 3-stage ring of 45 KB slot tiles (128 pairs, 22 double2 slots each) filled by TMA
 //             bulk copies (mbarrier full/empty pairs); the 16 warps of a CTA consume the same tile
 //             sequence, one RHS evaluation per warp per sweep, coupled only through the ring (a warp can
 //             run at most two tiles ahead), so every byte fetched from L2 is used by 16 trajectories.
@@ -48,8 +48,8 @@ struct StepArgs {
     toss_params p;
     UnitAxis axis;
     double Grho;
-    const double *pair_soa;    // [43][Ppad32]           (RESIDENT)
-    const double *pair_tiles;  // [n_tiles][43][128]     (STREAM)
+    const double *pair_soa;    // [22][Ppad32] double2 slots (RESIDENT)
+    const double *pair_tiles;  // [n_tiles][22][128] double2 (STREAM)
     const double *ray_soa;     // [9][Fpad32] faces in mesh order (global memory): the event-point ray test
     int Ppad32, n_tiles, last_tile_pairs;   // last_tile_pairs: real pairs of the last tile rounded up to 32
     int Fpad32;
@@ -95,6 +95,11 @@ __device__ __forceinline__ void refill_if_released(uint64_t *bars, int *claim, d
 // shared buffer; after a team barrier the owner adds N_A S_A + N_B S_B in the canonical order (row 0, 1, 2, ... of every tile).  The
 // arithmetic, and therefore every result bit, is the same for any team size.
 enum : int { kModeGrav = 0, kModeSkip = 1, kModeRetire = 2 };
+#ifdef K2_NO_COMPACT
+constexpr bool kCompactRows = false;   // developer A/B: per-lane loops over the out-of-range terms
+#else
+constexpr bool kCompactRows = true;
+#endif
 constexpr int kScratchDoubles = 96;             // pair_S scratch per warp: |G|[32] | l1+l2[32] | value[32]
 constexpr int kTeamBufDoubles = 4 + 2 * 4 * 64;   // P[3] + mode | S[2 buffers][4 rows][S_A x 32 lanes | S_B x 32 lanes]
 
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int team = wid / kTeam, rank = wid % kTeam;
-    const int mesh_doubles = kProxy ? 4 * a.proxy_n : (kStream ? kK2Stages * kPairTileDoubles : kPairFields * a.Ppad32);
+    const int mesh_doubles = kProxy ? 4 * a.proxy_n : (kStream ? kK2Stages * kPairTileDoubles : 2 * kPairSlots * a.Ppad32);
     double *mesh = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(mesh + mesh_doubles);   // full[3] empty[3] (STREAM) / full[1]
     double *wstate = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)wid * warp_state_doubles(a.n_man);
@@ -196,11 +201,11 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     const int rows = ((tl == a.n_tiles - 1) ? a.last_tile_pairs : kPairTile) >> 5;
                     mbar_wait(&bars[s], (it / kK2Stages) & 1u);
                     if (mode == kModeGrav) {
-                        const double *tile = mesh + (size_t)s * kPairTileDoubles + lane;
+                        const double2 *tile = reinterpret_cast<const double2 *>(mesh + (size_t)s * kPairTileDoubles) + lane;
                         for (int r = rank; r < rows; r += kTeam) {
-                            const double *col = tile + 32 * r;
+                            const PairCols<false> cols{tile + 32 * r, kPairTile};
                             double SA, SB, hpA, hpB;
-                            pair_S<true>([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, SA, SB, hpA, hpB, scr);
+                            pair_S<kCompactRows>(cols, Px, Py, Pz, SA, SB, hpA, hpB, scr);
                             sbuf[(spar * 4 + r) * 64 + lane] = SA;
                             sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                         }
@@ -218,9 +223,9 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 for (int v = 0; v * 4 < rows_total; ++v) {
                     const int rows = rows_total - 4 * v < 4 ? rows_total - 4 * v : 4;
                     for (int r = rank; r < rows; r += kTeam) {
-                        const double *col = mesh + 32 * (4 * v + r) + lane;
+                        const PairCols<false> cols{reinterpret_cast<const double2 *>(mesh) + 32 * (4 * v + r) + lane, Fp};
                         double SA, SB, hpA, hpB;
-                        pair_S<true>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, SA, SB, hpA, hpB, scr);
+                        pair_S<kCompactRows>(cols, Px, Py, Pz, SA, SB, hpA, hpB, scr);
                         sbuf[(spar * 4 + r) * 64 + lane] = SA;
                         sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                     }
@@ -438,30 +443,30 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     // the ray test ran on the global face table above; this sweep only keeps step with the ring
                 } else if (active && kTeam > 1) {
                     // team sweep: S of my rows into the buffer, barrier, then N S of ALL rows in canonical order
-                    const double *tile = mesh + (size_t)s * kPairTileDoubles + lane;
+                    const double2 *tile = reinterpret_cast<const double2 *>(mesh + (size_t)s * kPairTileDoubles) + lane;
                     const int rows = f_end >> 5;
                     for (int r = 0; r < rows; r += kTeam) {
-                        const double *col = tile + 32 * r;
+                        const PairCols<false> cols{tile + 32 * r, kPairTile};
                         double SA, SB, hpA, hpB;
-                        pair_S<true>([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, SA, SB, hpA, hpB, scr);
+                        pair_S<kCompactRows>(cols, Px, Py, Pz, SA, SB, hpA, hpB, scr);
                         sbuf[(spar * 4 + r) * 64 + lane] = SA;
                         sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                     }
                     team_bar(team, 32 * kTeam);
                     for (int r = 0; r < rows; ++r) {
-                        const double *col = tile + 32 * r;
+                        const PairCols<false> cols{tile + 32 * r, kPairTile};
                         const double SA = sbuf[(spar * 4 + r) * 64 + lane], SB = sbuf[(spar * 4 + r) * 64 + 32 + lane];
-                        ax = fma(col[15 * kPairTile], SB, fma(col[12 * kPairTile], SA, ax));
-                        ay = fma(col[16 * kPairTile], SB, fma(col[13 * kPairTile], SA, ay));
-                        az = fma(col[17 * kPairTile], SB, fma(col[14 * kPairTile], SA, az));
+                        ax = fma(cols(15), SB, fma(cols(12), SA, ax));
+                        ay = fma(cols(16), SB, fma(cols(13), SA, ay));
+                        az = fma(cols(17), SB, fma(cols(14), SA, az));
                     }
                     spar ^= 1;
                 } else if (active) {
-                    const double *tile = mesh + (size_t)s * kPairTileDoubles + lane;
+                    const double2 *tile = reinterpret_cast<const double2 *>(mesh + (size_t)s * kPairTileDoubles) + lane;
 #pragma unroll kK2Unroll
                     for (int f = 0; f < f_end; f += 32) {
-                        const double *col = tile + f;
-                        pair_term<false, true>([col](int k) { return col[k * kPairTile]; }, Px, Py, Pz, ax, ay, az, pv, scr);
+                        const PairCols<false> cols{tile + f, kPairTile};
+                        pair_term<false, kCompactRows>(cols, Px, Py, Pz, ax, ay, az, pv, scr);
                     }
                 }
                 __syncwarp();
@@ -484,27 +489,27 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 for (int v = 0; v * 4 < rows_total; ++v) {
                     const int rows = rows_total - 4 * v < 4 ? rows_total - 4 * v : 4;
                     for (int r = 0; r < rows; r += kTeam) {
-                        const double *col = mesh + 32 * (4 * v + r) + lane;
+                        const PairCols<false> cols{reinterpret_cast<const double2 *>(mesh) + 32 * (4 * v + r) + lane, Fp};
                         double SA, SB, hpA, hpB;
-                        pair_S<true>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, SA, SB, hpA, hpB, scr);
+                        pair_S<kCompactRows>(cols, Px, Py, Pz, SA, SB, hpA, hpB, scr);
                         sbuf[(spar * 4 + r) * 64 + lane] = SA;
                         sbuf[(spar * 4 + r) * 64 + 32 + lane] = SB;
                     }
                     team_bar(team, 32 * kTeam);
                     for (int r = 0; r < rows; ++r) {
-                        const double *col = mesh + 32 * (4 * v + r) + lane;
+                        const PairCols<false> cols{reinterpret_cast<const double2 *>(mesh) + 32 * (4 * v + r) + lane, Fp};
                         const double SA = sbuf[(spar * 4 + r) * 64 + lane], SB = sbuf[(spar * 4 + r) * 64 + 32 + lane];
-                        ax = fma(col[15 * Fp], SB, fma(col[12 * Fp], SA, ax));
-                        ay = fma(col[16 * Fp], SB, fma(col[13 * Fp], SA, ay));
-                        az = fma(col[17 * Fp], SB, fma(col[14 * Fp], SA, az));
+                        ax = fma(cols(15), SB, fma(cols(12), SA, ax));
+                        ay = fma(cols(16), SB, fma(cols(13), SA, ay));
+                        az = fma(cols(17), SB, fma(cols(14), SA, az));
                     }
                     spar ^= 1;
                 }
             } else {
 #pragma unroll kK2Unroll
                 for (int f = lane; f < Fp; f += 32) {
-                    const double *col = mesh + f;
-                    pair_term<false, true>([col, Fp](int k) { return col[k * Fp]; }, Px, Py, Pz, ax, ay, az, pv, scr);
+                    const PairCols<false> cols{reinterpret_cast<const double2 *>(mesh) + f, Fp};
+                    pair_term<false, kCompactRows>(cols, Px, Py, Pz, ax, ay, az, pv, scr);
                 }
             }
         }
@@ -523,9 +528,9 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         // k_stage = [ys[3..5], -g_pkg]   (equations_of_motion.py:59,92-95)
         double kc = 0.0;
         if (lane < 3) kc = vsh;
-        else if (lane == 3) kc = kProxy ? ax : -(a.Grho * ax);
-        else if (lane == 4) kc = kProxy ? ay : -(a.Grho * ay);
-        else if (lane == 5) kc = kProxy ? az : -(a.Grho * az);
+        else if (lane == 3) kc = kProxy ? ax : -((a.Grho + a.Grho) * ax);   // the pair sum runs in exact halves
+        else if (lane == 4) kc = kProxy ? ay : -((a.Grho + a.Grho) * ay);
+        else if (lane == 5) kc = kProxy ? az : -((a.Grho + a.Grho) * az);
         if (lane < 6) sk[6 * stage + lane] = kc;
         __syncwarp();
         if (stage == 0) {
@@ -812,7 +817,7 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
 
     const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 +
                                (size_t)(kK2Warps / 2) * kTeamBufDoubles * 8 + (size_t)kK2Warps * kScratchDoubles * 8;
-    const size_t resident_bytes = (size_t)kPairFields * ctx->Ppad32 * 8 + state_bytes;
+    const size_t resident_bytes = (size_t)2 * kPairSlots * ctx->Ppad32 * 8 + state_bytes;
     const size_t stream_bytes = (size_t)kK2Stages * kPairTileBytes + state_bytes;
     const bool resident = resident_bytes <= (size_t)(200 / K2_MINBLOCKS) * 1024;   // every CTA on an SM keeps its own copy
     const int per_cta = kK2Warps / team;
