@@ -314,10 +314,11 @@ def run_ours(args):
                          "peak_source": "measured live: register-resident DFMA chains on all SMs (toss_measure_fp64_peak); "
                                         "MEASURED_PEAKS.json has no FP64 entry",
                          "algorithmic_flops_per_launch": alg_flops_per_launch, "kernel_ms": kernel_ms,
-                         "traffic": 17.8e3 * (hi - lo),
-                         "traffic_note": "DRAM bytes per launch = 17.8 KB per trajectory (the knots), from the ncu capture "
-                                         "profiles/r1d_stepper_ncu_details.csv (291 MB at 16384 trajectories); the mesh is "
-                                         "L2 / shared-memory resident -- the bound is the FP64 pipe, not HBM",
+                         "traffic": 17.6e3 * (hi - lo),
+                         "traffic_note": "DRAM bytes per launch = 17.6 KB per trajectory (the knots), from the ncu capture "
+                                         "profiles/r1i_stepper_ncu_details.csv (28.9 MB read + 260.1 MB written at 16384 "
+                                         "trajectories); the mesh is L2 / shared-memory resident -- the bound is the FP64 "
+                                         "pipe's issue rate, not HBM",
                          "note": f"algorithmic = gravity evaluations x {F} faces x {W_FACE} ops (SURVEY.md 8d)"},
         }
         if not args.no_microbench:

@@ -18,6 +18,8 @@ for v in "$@"; do
     w24)    build w24 -DK2_WARPS=24 ;;
     hint)   build hint -DK2_WAIT_HINT=20000 ;;
     nocompact) build nocompact -DK2_NO_COMPACT ;;
+    w8x2s2) build w8x2s2 -DK2_WARPS=8 -DK2_MINBLOCKS=2 -DK2_STAGES=2 -DK2_NO_TEAMBUF ;;
+    s4nt)   build s4nt -DK2_STAGES=4 -DK2_NO_TEAMBUF ;;
     prof)   build prof -DK2_PROFILE ;;
     prof4)  build prof4 -DK2_PROFILE -DK2_STAGES=4 ;;
     *) echo "unknown variant $v"; exit 1 ;;

@@ -1,5 +1,6 @@
 import os, sys; from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
+os.environ.setdefault("TOSS_B200_LPT", "0")   # the instrumented counters share the queue area with the order arrays
 os.environ["TOSS_B200_LIB"] = str(ROOT / "build" / "variants" / (sys.argv[2] if len(sys.argv) > 2 else "libtoss_prof.so"))
 sys.path.insert(0, str(ROOT))
 import numpy as np, torch

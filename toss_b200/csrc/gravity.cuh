@@ -70,15 +70,6 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
     const double qB = numB * iB;
     const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
     const double qAs = qA * qA, qBs = qB * qB;
-    // HALF values from here on: atanh(z) and atan(q) instead of 2 atanh(z) = LN and 2 atan(q) = omega.  Scaling by
-    // 2 is exact, so S/2 and the accumulated sum/2 carry the same bits; the callers multiply by 2 G rho at the end.
-    double ln0 = tm_atanh_mm(z0, z0s);
-    double ln1 = tm_atanh_mm(z1, z1s);
-    double ln2 = tm_atanh_mm(z2, z2s);
-    double ln3 = tm_atanh_mm(z3, z3s);
-    double ln4 = tm_atanh_mm(z4, z4s);
-    double omA = tm_atan_mm(qA, qAs);
-    double omB = tm_atan_mm(qB, qBs);
     // Range tests.  An edge seen under a large angle (z^2 >= kZ2Max) takes a division of its own and the ln-based
     // atanh; a face seen under a large solid angle or from behind (den <= 0 or q^2 >= kQ2Max) the full-range atan2.
     // Each term chooses for itself; the rule is part of the arithmetic specification.  The
@@ -92,6 +83,19 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
               hdB = __double2hiint(denB);
     const bool anybad = (max(max(max(hz0, hz1), hz2), max(hz3, hz4)) >= kHiZ2Max) | (max(hqA, hqB) >= kHiQ2Max) |
                         (min(hdA, hdB) <= 0);
+    // the warp vote is issued BEFORE the polynomials so that its latency (integer maxima -> compare -> vote) hides
+    // behind them instead of sitting at the end of the row with nothing left to issue
+    constexpr unsigned kFull = 0xffffffffu;
+    const bool warp_bad = kCompact ? (__any_sync(kFull, anybad) != 0) : false;
+    // HALF values from here on: atanh(z) and atan(q) instead of 2 atanh(z) = LN and 2 atan(q) = omega.  Scaling by
+    // 2 is exact, so S/2 and the accumulated sum/2 carry the same bits; the callers multiply by 2 G rho at the end.
+    double ln0 = tm_atanh_mm(z0, z0s);
+    double ln1 = tm_atanh_mm(z1, z1s);
+    double ln2 = tm_atanh_mm(z2, z2s);
+    double ln3 = tm_atanh_mm(z3, z3s);
+    double ln4 = tm_atanh_mm(z4, z4s);
+    double omA = tm_atan_mm(qA, qAs);
+    double omB = tm_atan_mm(qB, qBs);
     unsigned bad = 0u, badw = 0u;
     if (kCompact) {
         // Out-of-range terms are rare (a pair within a few hundred metres of the field point; ~1.4 % of the 32-pair
@@ -101,8 +105,7 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
         // owners read the values back -- ceil(#terms / 32) general evaluations per row instead of
         // max-over-lanes(#terms of a lane).  Same operations on the same operands: the values do not depend on who
         // computes them.
-        constexpr unsigned kFull = 0xffffffffu;
-        if (__any_sync(kFull, anybad)) {
+        if (warp_bad) {
             bad = (hz0 < kHiZ2Max ? 0u : 1u) | (hz1 < kHiZ2Max ? 0u : 2u) | (hz2 < kHiZ2Max ? 0u : 4u) |
                   (hz3 < kHiZ2Max ? 0u : 8u) | (hz4 < kHiZ2Max ? 0u : 16u);
             badw = ((hdA > 0 && hqA < kHiQ2Max) ? 0u : 1u) | ((hdB > 0 && hqB < kHiQ2Max) ? 0u : 2u);

@@ -101,6 +101,11 @@ constexpr bool kCompactRows = false;   // developer A/B: per-lane loops over the
 constexpr bool kCompactRows = true;
 #endif
 constexpr int kScratchDoubles = 96;             // pair_S scratch per warp: |G|[32] | l1+l2[32] | value[32]
+#ifdef K2_NO_TEAMBUF
+constexpr int kTeamBufs = 0;               // developer experiment (team size 1 only): no team mailboxes
+#else
+constexpr int kTeamBufs = kK2Warps / 2;    // one mailbox per team of two (the most teams a CTA can hold)
+#endif
 constexpr int kTeamBufDoubles = 4 + 2 * 4 * 64;   // P[3] + mode | S[2 buffers][4 rows][S_A x 32 lanes | S_B x 32 lanes]
 
 __device__ __forceinline__ void team_bar(int team, int nthreads)
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                    (size_t)team * kTeamBufDoubles;                       // team mailbox: P, mode, S buffers
     // per-warp scratch of pair_S (compaction of the out-of-range edge terms of a row): 96 doubles
     double *scr = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)kK2Warps * warp_state_doubles(a.n_man) +
-                  (size_t)(kK2Warps / 2) * kTeamBufDoubles + (size_t)wid * kScratchDoubles;
+                  (size_t)kTeamBufs * kTeamBufDoubles + (size_t)wid * kScratchDoubles;
     volatile double *tP = tbuf;
     volatile int *tmode = reinterpret_cast<volatile int *>(tbuf + 3);
     double *sbuf = tbuf + 4;
@@ -802,7 +807,7 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
         if (px.p.rtol < ptol) px.p.rtol = ptol;
         if (px.p.atol < ptol) px.p.atol = ptol;
         const size_t psmem = (size_t)4 * ctx->n_mascons * 8 + (size_t)kK2Warps * warp_state_doubles(n_man) * 8 +
-                             kK2BarSlots * 8 + (size_t)(kK2Warps / 2) * kTeamBufDoubles * 8 +
+                             kK2BarSlots * 8 + (size_t)kTeamBufs * kTeamBufDoubles * 8 +
                              (size_t)kK2Warps * kScratchDoubles * 8;
         int pctas = (pop + kK2Warps - 1) / kK2Warps;
         if (pctas > K2_MINBLOCKS * ctx->sm_count) pctas = K2_MINBLOCKS * ctx->sm_count;
@@ -816,7 +821,7 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     }
 
     const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 +
-                               (size_t)(kK2Warps / 2) * kTeamBufDoubles * 8 + (size_t)kK2Warps * kScratchDoubles * 8;
+                               (size_t)kTeamBufs * kTeamBufDoubles * 8 + (size_t)kK2Warps * kScratchDoubles * 8;
     const size_t resident_bytes = (size_t)2 * kPairSlots * ctx->Ppad32 * 8 + state_bytes;
     const size_t stream_bytes = (size_t)kK2Stages * kPairTileBytes + state_bytes;
     const bool resident = resident_bytes <= (size_t)(200 / K2_MINBLOCKS) * 1024;   // every CTA on an SM keeps its own copy
