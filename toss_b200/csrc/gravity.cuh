@@ -96,7 +96,7 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
     double ln4 = tm_atanh_mm(z4, z4s);
     double omA = tm_atan_mm(qA, qAs);
     double omB = tm_atan_mm(qB, qBs);
-    unsigned bad = 0u, badw = 0u;
+    unsigned badw = 0u;
     if (kCompact) {
         // Out-of-range terms are rare (a pair within a few hundred metres of the field point; ~1.4 % of the 32-pair
         // rows of an init-like population have any, then ~13 edge terms spread over ~5 lanes).  In the stepper every
@@ -106,8 +106,8 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
         // max-over-lanes(#terms of a lane).  Same operations on the same operands: the values do not depend on who
         // computes them.
         if (warp_bad) {
-            bad = (hz0 < kHiZ2Max ? 0u : 1u) | (hz1 < kHiZ2Max ? 0u : 2u) | (hz2 < kHiZ2Max ? 0u : 4u) |
-                  (hz3 < kHiZ2Max ? 0u : 8u) | (hz4 < kHiZ2Max ? 0u : 16u);
+            const unsigned bad = (hz0 < kHiZ2Max ? 0u : 1u) | (hz1 < kHiZ2Max ? 0u : 2u) | (hz2 < kHiZ2Max ? 0u : 4u) |
+                                 (hz3 < kHiZ2Max ? 0u : 8u) | (hz4 < kHiZ2Max ? 0u : 16u);
             badw = ((hdA > 0 && hqA < kHiQ2Max) ? 0u : 1u) | ((hdB > 0 && hqB < kHiQ2Max) ? 0u : 2u);
             const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
             const unsigned b0 = __ballot_sync(kFull, bad & 1u), b1 = __ballot_sync(kFull, bad & 2u),
@@ -134,26 +134,18 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
                 if ((bad & 16u) && p4 - base < 32u) ln4 = sv[p4 - base];
                 __syncwarp();
             }
-            bad = 0u;
         }
     } else if (anybad) {
-        bad = (hz0 < kHiZ2Max ? 0u : 1u) | (hz1 < kHiZ2Max ? 0u : 2u) | (hz2 < kHiZ2Max ? 0u : 4u) |
-              (hz3 < kHiZ2Max ? 0u : 8u) | (hz4 < kHiZ2Max ? 0u : 16u);
+        // callers without a converged warp (thread-per-point kernel: 32 different field points): every lane fixes
+        // its own terms
+        if (hz0 >= kHiZ2Max) ln0 = 0.5 * tm_two_atanh(tm_div(G0, a0));
+        if (hz1 >= kHiZ2Max) ln1 = 0.5 * tm_two_atanh(tm_div(G1, a1));
+        if (hz2 >= kHiZ2Max) ln2 = 0.5 * tm_two_atanh(tm_div(G2, a2));
+        if (hz3 >= kHiZ2Max) ln3 = 0.5 * tm_two_atanh(tm_div(G3, a3));
+        if (hz4 >= kHiZ2Max) ln4 = 0.5 * tm_two_atanh(tm_div(G4, a4));
         badw = ((hdA > 0 && hqA < kHiQ2Max) ? 0u : 1u) | ((hdB > 0 && hqB < kHiQ2Max) ? 0u : 2u);
     }
-    while (bad) {   // per-lane walk through the bad edge terms (callers without a converged warp)
-        const unsigned k = __ffs(bad) - 1;
-        bad &= bad - 1;
-        const double Gk = k == 0 ? G0 : k == 1 ? G1 : k == 2 ? G2 : k == 3 ? G3 : G4;
-        const double ak = k == 0 ? a0 : k == 1 ? a1 : k == 2 ? a2 : k == 3 ? a3 : a4;
-        const double v = 0.5 * tm_two_atanh(tm_div(Gk, ak));
-        if (k == 0) ln0 = v;
-        else if (k == 1) ln1 = v;
-        else if (k == 2) ln2 = v;
-        else if (k == 3) ln3 = v;
-        else ln4 = v;
-    }
-    while (badw) {
+    while (badw) {   // solid-angle terms out of range: 0.4 per row that has any bad term -- not worth compacting
         const bool isA = badw & 1u;
         badw &= badw - 1;
         const double v = tm_atan2(isA ? numA : numB, isA ? denA : denB);
