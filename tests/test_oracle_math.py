@@ -61,3 +61,19 @@ def test_roots():
     x = 10.0 ** rng.uniform(-30, 30, 200000)
     assert ulps(O.math_probe("root8", x), x ** 0.125).max() <= 2
     assert ulps(O.math_probe("root4", x), x ** 0.25).max() <= 2
+
+
+def test_high_word_thresholds_of_the_range_tests():
+    """The pair sum tests `z^2 < 0x3FA47AE1'00000000` and `q^2 < 0x3F847AE1'00000000` on the high words: the constants
+    are the high words of 0.04 and 0.01, the thresholds sit just below them (inside the range the polynomials were
+    fitted on), and for non-negative doubles the high-word order is the value order."""
+    hi = lambda x: int(np.float64(x).view(np.uint64) >> np.uint64(32))
+    assert hi(0.04) == 0x3FA47AE1 and hi(0.01) == 0x3F847AE1
+    tz = np.uint64(0x3FA47AE100000000).view(np.float64)
+    tq = np.uint64(0x3F847AE100000000).view(np.float64)
+    assert 0.04 - 1e-9 < tz < 0.04 and 0.01 - 3e-10 < tq < 0.01
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.uniform(0, 0.1, 100000), tz + np.arange(-50, 50) * np.spacing(tz), [0.0, np.inf, np.nan]])
+    hw = (x.view(np.uint64) >> np.uint64(32)).astype(np.int64)
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(hw < 0x3FA47AE1, x < tz)          # NaN and inf fail both
