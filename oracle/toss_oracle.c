@@ -406,8 +406,8 @@ static inline void pair_term(const double *rc, const double P[3], double *ax, do
     const double qA = (numA * a2) * i2A;
     const double z3 = (G[3] * a4) * i34, z4 = (G[4] * a3) * i34;
     const double qB = numB * iB;
-    /* Range tests: the thresholds are doubles whose low word is 0 (0x3FA47AE1'00000000 = 0.04 - 9e-10 for z^2,
-     * 0x3F847AE1'00000000 = 0.01 - 2e-10 for q^2), so for x >= 0 `x < threshold` is a comparison of the high words
+    /* Range tests: the thresholds are doubles whose low word is 0 (0x3FA47AE1'00000000 = 0.04 - 8.3e-9 for z^2,
+     * 0x3F847AE1'00000000 = 0.01 - 2.1e-9 for q^2), so for x >= 0 `x < threshold` is a comparison of the high words
      * (the CUDA side does it on the integer pipe); a NaN fails it; `den > 0` likewise reads hi(den) > 0. */
     const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
     const double qAs = qA * qA, qBs = qB * qB;

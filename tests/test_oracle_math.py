@@ -71,7 +71,7 @@ def test_high_word_thresholds_of_the_range_tests():
     assert hi(0.04) == 0x3FA47AE1 and hi(0.01) == 0x3F847AE1
     tz = np.uint64(0x3FA47AE100000000).view(np.float64)
     tq = np.uint64(0x3F847AE100000000).view(np.float64)
-    assert 0.04 - 1e-9 < tz < 0.04 and 0.01 - 3e-10 < tq < 0.01
+    assert 0.04 - 1e-8 < tz < 0.04 and 0.01 - 3e-9 < tq < 0.01
     rng = np.random.default_rng(11)
     x = np.concatenate([rng.uniform(0, 0.1, 100000), tz + np.arange(-50, 50) * np.spacing(tz), [0.0, np.inf, np.nan]])
     hw = (x.view(np.uint64) >> np.uint64(32)).astype(np.int64)
