@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     uint32_t tile_it = 0;     // tiles consumed so far by this warp (== by every warp: lock step)
 
     // warp-uniform trajectory state
-    bool active = false, queue_empty = false, counted_out = false;
+    bool active = false, queue_empty = false, counted_out = false, first_fetch = true;
     int traj = -1, stage = 0, seg = 0, nseg = 0, nk = 0, steps = 0, clipped = 0, after_accept = 0, status = 0;
     int n_acc = 0, n_rej = 0, n_ev = 0, collided = 0, stopped = 0, ray_sweep = 0;
     long long n_rhs = 0;
@@ -258,9 +258,18 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     for (;;) {
         // ------------------------------------------------ fetch a trajectory, decode the chromosome
         if (!active && !queue_empty) {
+            // The first trajectory of every team is assigned statically, team t of CTA b takes queue position
+            // b + gridDim.x * t: a population smaller than the machine spreads over ALL SMs (a warp that shares its
+            // scheduler with fewer warps runs faster) instead of filling the first CTAs; later ones come from the
+            // atomic cursor, which starts behind the static round.
             int nxt = 0;
-            if (lane == 0) nxt = atomicAdd(a.queue, 1);
-            nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            if (first_fetch) {
+                nxt = (int)blockIdx.x + (int)gridDim.x * team;
+                first_fetch = false;
+            } else {
+                if (lane == 0) nxt = atomicAdd(a.queue, 1) + (int)gridDim.x * (kK2Warps / kTeam);
+                nxt = __shfl_sync(0xffffffffu, nxt, 0);
+            }
             if (nxt >= a.pop) {
                 queue_empty = true;
             } else {
@@ -784,6 +793,10 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     // not depend on it.
     const int slots = K2_MINBLOCKS * ctx->sm_count * kK2Warps;
     int team = pop >= 6 * slots ? 1 : (2 * pop >= 3 * slots ? 2 : 4);
+    // a team splits the 32-pair ROWS of the table: more warps than rows only adds barrier hand-shakes (lllp: 1 row)
+    const int rows = ctx->Ppad32 / 32;
+    if (rows < 2) team = 1;
+    else if (rows < 3 && team > 2) team = 2;
     if (const char *e = getenv("TOSS_B200_TEAM")) team = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1);   // developer override
     // longest-first queue order when trajectories queue for warps (otherwise order is irrelevant) and the mesh is
     // large enough that the proxy run is cheap next to the real one (lp pop 32768: 1292 -> 1220 ms)
@@ -809,8 +822,7 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
         const size_t psmem = (size_t)4 * ctx->n_mascons * 8 + (size_t)kK2Warps * warp_state_doubles(n_man) * 8 +
                              kK2BarSlots * 8 + (size_t)kTeamBufs * kTeamBufDoubles * 8 +
                              (size_t)kK2Warps * kScratchDoubles * 8;
-        int pctas = (pop + kK2Warps - 1) / kK2Warps;
-        if (pctas > K2_MINBLOCKS * ctx->sm_count) pctas = K2_MINBLOCKS * ctx->sm_count;
+        const int pctas = pop < K2_MINBLOCKS * ctx->sm_count ? pop : K2_MINBLOCKS * ctx->sm_count;
         TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)psmem));
         stepper_kernel<false, 1, true><<<pctas, kK2Threads, psmem, st>>>(px);
@@ -825,10 +837,9 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     const size_t resident_bytes = (size_t)2 * kPairSlots * ctx->Ppad32 * 8 + state_bytes;
     const size_t stream_bytes = (size_t)kK2Stages * kPairTileBytes + state_bytes;
     const bool resident = resident_bytes <= (size_t)(200 / K2_MINBLOCKS) * 1024;   // every CTA on an SM keeps its own copy
-    const int per_cta = kK2Warps / team;
-    int ctas = (pop + per_cta - 1) / per_cta;
+    // one CTA per SM as soon as there is a trajectory for it (the static first round spreads them over the CTAs)
     const int max_ctas = K2_MINBLOCKS * ctx->sm_count;
-    if (ctas > max_ctas) ctas = max_ctas;
+    const int ctas = pop < max_ctas ? pop : max_ctas;
     const size_t smem = resident ? resident_bytes : stream_bytes;
 #define TOSS_LAUNCH_STEPPER(STREAM, TEAM)                                                                          \
     do {                                                                                                           \
