@@ -41,6 +41,21 @@ static inline double orc_two_atan_mm(double t, double t2) /* 2 atan(t) */
     const double tt = t + t;
     return ORC_FMA(tt * t2, p, tt);
 }
+/* far tier of the face-pair sum: 4 coefficients for z*z, t*t <= 0.0025 (approximation error 2.0e-17 of the value) */
+static inline double orc_two_atanh_far(double z, double z2)
+{
+    double p = ORC_ATANH_FAR[3];
+    for (int k = 2; k >= 0; --k) p = ORC_FMA(p, z2, ORC_ATANH_FAR[k]);
+    const double zz = z + z;
+    return ORC_FMA(zz * z2, p, zz);
+}
+static inline double orc_two_atan_far(double t, double t2)
+{
+    double p = ORC_ATAN_FAR[3];
+    for (int k = 2; k >= 0; --k) p = ORC_FMA(p, t2, ORC_ATAN_FAR[k]);
+    const double tt = t + t;
+    return ORC_FMA(tt * t2, p, tt);
+}
 static inline double orc_two_atanh_series(double z) { return orc_two_atanh_series_n(z, z * z, 11); }
 
 /* ln(x), x > 0 normal: x = 2^e m, m in [sqrt(1/2), sqrt(2)); ln m = 2 atanh((m-1)/(m+1)) */

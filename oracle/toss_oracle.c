@@ -356,13 +356,22 @@ static void gravity_point_direct(const orc_mesh *m, const double P[3], double ac
  * to a division of its own + ln-based atanh, or to the full-range atan2. */
 #define ORC_HI_Z2MAX 0x3FA47AE1
 #define ORC_HI_Q2MAX 0x3F847AE1
+#define ORC_HI_FAR 0x3F647AE1 /* high word of 0.0025: z^2, q^2 < 0x3F647AE1'00000000 = 0.0025 - 5.2e-10 */
 static inline int32_t orc_hi(double x)   /* high word of the IEEE-754 pattern, as a signed integer */
 {
     uint64_t b;
     memcpy(&b, &x, 8);
     return (int32_t)(b >> 32);
 }
-static inline void pair_term(const double *rc, const double P[3], double *ax, double *ay, double *az, double *pv)
+
+/* Everything of a pair term up to the arguments of the transcendental functions. */
+typedef struct {
+    const double *rc;
+    double hpA, hpB, hA0, hA1, hA2, hB0, hB1, hB2;
+    double a[5], z[5], zs[5], q[2], qs[2], num[2], den[2];
+} pair_pre;
+
+static inline void pair_prelim(const double *rc, const double P[3], pair_pre *o)
 {
     const double r0x = rc[0] - P[0], r0y = rc[1] - P[1], r0z = rc[2] - P[2];
     const double r1x = rc[3] - P[0], r1y = rc[4] - P[1], r1z = rc[5] - P[2];
@@ -373,14 +382,15 @@ static inline void pair_term(const double *rc, const double P[3], double *ax, do
     const double l2 = sqrt(ORC_FMA(r2z, r2z, ORC_FMA(r2y, r2y, r2x * r2x)));
     const double l3 = sqrt(ORC_FMA(r3z, r3z, ORC_FMA(r3y, r3y, r3x * r3x)));
     const double *NA = rc + 12, *NB = rc + 15, *nA = rc + 18, *nB = rc + 27, *G = rc + 36;
-    const double hpA = ORC_FMA(NA[2], r0z, ORC_FMA(NA[1], r0y, NA[0] * r0x));
-    const double hpB = ORC_FMA(NB[2], r1z, ORC_FMA(NB[1], r1y, NB[0] * r1x));
-    const double hA0 = ORC_FMA(nA[2], r0z, ORC_FMA(nA[1], r0y, nA[0] * r0x));
-    const double hA1 = ORC_FMA(nA[5], r1z, ORC_FMA(nA[4], r1y, nA[3] * r1x));
-    const double hA2 = ORC_FMA(nA[8], r2z, ORC_FMA(nA[7], r2y, nA[6] * r2x));
-    const double hB0 = ORC_FMA(nB[2], r1z, ORC_FMA(nB[1], r1y, nB[0] * r1x));
-    const double hB1 = ORC_FMA(nB[5], r0z, ORC_FMA(nB[4], r0y, nB[3] * r0x));
-    const double hB2 = ORC_FMA(nB[8], r3z, ORC_FMA(nB[7], r3y, nB[6] * r3x));
+    o->rc = rc;
+    o->hpA = ORC_FMA(NA[2], r0z, ORC_FMA(NA[1], r0y, NA[0] * r0x));
+    o->hpB = ORC_FMA(NB[2], r1z, ORC_FMA(NB[1], r1y, NB[0] * r1x));
+    o->hA0 = ORC_FMA(nA[2], r0z, ORC_FMA(nA[1], r0y, nA[0] * r0x));
+    o->hA1 = ORC_FMA(nA[5], r1z, ORC_FMA(nA[4], r1y, nA[3] * r1x));
+    o->hA2 = ORC_FMA(nA[8], r2z, ORC_FMA(nA[7], r2y, nA[6] * r2x));
+    o->hB0 = ORC_FMA(nB[2], r1z, ORC_FMA(nB[1], r1y, nB[0] * r1x));
+    o->hB1 = ORC_FMA(nB[5], r0z, ORC_FMA(nB[4], r0y, nB[3] * r0x));
+    o->hB2 = ORC_FMA(nB[8], r3z, ORC_FMA(nB[7], r3y, nB[6] * r3x));
     const double a0 = l0 + l1, a1 = l1 + l2, a2 = l2 + l0, a3 = l0 + l3, a4 = l3 + l1;
     const double d01 = ORC_FMA(r0z, r1z, ORC_FMA(r0y, r1y, r0x * r1x));
     const double d12 = ORC_FMA(r1z, r2z, ORC_FMA(r1y, r2y, r1x * r2x));
@@ -390,52 +400,86 @@ static inline void pair_term(const double *rc, const double P[3], double *ax, do
     const double l01 = l0 * l1;
     const double denA = ORC_FMA(l2, d01, ORC_FMA(l1, d20, ORC_FMA(l0, d12, l01 * l2)));
     const double denB = ORC_FMA(l3, d01, ORC_FMA(l0, d31, ORC_FMA(l1, d03, l01 * l3)));
-    const double numA = hpA * rc[41], numB = hpB * rc[42];
+    const double numA = o->hpA * rc[41], numB = o->hpB * rc[42];
     /* One division serves the five edge quotients and the two solid-angle quotients (X Y is a product of lengths
      * and of the two solid-angle denominators: it only has to be non-zero; were a denominator exactly 0 every
-     * quotient would come out non-finite, fail its range test and take its own way).  An edge seen under a large
-     * angle takes a division of its own and the ln-based atanh, a face seen under a large solid angle (or from
-     * behind) the full-range atan2.  Each term chooses for itself, so a close face costs only the terms that need
-     * it. */
+     * quotient would come out non-finite, fail its range test and take its own way). */
     const double P01 = a0 * a1, P2A = a2 * denA, P34 = a3 * a4;
     const double X = P01 * P2A, Y = P34 * denB;
     const double inv = 1.0 / (X * Y);
     const double iX = Y * inv, iY = X * inv;
     const double i01 = P2A * iX, i2A = P01 * iX, i34 = denB * iY, iB = P34 * iY;
-    const double z0 = (G[0] * a1) * i01, z1 = (G[1] * a0) * i01, z2 = (G[2] * denA) * i2A;
-    const double qA = (numA * a2) * i2A;
-    const double z3 = (G[3] * a4) * i34, z4 = (G[4] * a3) * i34;
-    const double qB = numB * iB;
-    /* Range tests: the thresholds are doubles whose low word is 0 (0x3FA47AE1'00000000 = 0.04 - 8.3e-9 for z^2,
-     * 0x3F847AE1'00000000 = 0.01 - 2.1e-9 for q^2), so for x >= 0 `x < threshold` is a comparison of the high words
-     * (the CUDA side does it on the integer pipe); a NaN fails it; `den > 0` likewise reads hi(den) > 0. */
-    const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
-    const double qAs = qA * qA, qBs = qB * qB;
-    const int okA = (orc_hi(denA) > 0) && (orc_hi(qAs) < ORC_HI_Q2MAX);
-    const int okB = (orc_hi(denB) > 0) && (orc_hi(qBs) < ORC_HI_Q2MAX);
-    const double ln0 = (orc_hi(z0s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z0, z0s) : orc_two_atanh(G[0] / a0);
-    const double ln1 = (orc_hi(z1s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z1, z1s) : orc_two_atanh(G[1] / a1);
-    const double ln2 = (orc_hi(z2s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z2, z2s) : orc_two_atanh(G[2] / a2);
-    const double ln3 = (orc_hi(z3s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z3, z3s) : orc_two_atanh(G[3] / a3);
-    const double ln4 = (orc_hi(z4s) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(z4, z4s) : orc_two_atanh(G[4] / a4);
-    const double omA = okA ? orc_two_atan_mm(qA, qAs) : 2.0 * orc_atan2(numA, denA);
-    const double omB = okB ? orc_two_atan_mm(qB, qBs) : 2.0 * orc_atan2(numB, denB);
-    const double SA = ORC_FMA(-hpA, omA, ORC_FMA(hA2, ln2, ORC_FMA(hA1, ln1, hA0 * ln0)));
-    const double SB = ORC_FMA(-hpB, omB, ORC_FMA(hB2, ln4, ORC_FMA(hB1, ln3, hB0 * ln0)));
+    o->z[0] = (G[0] * a1) * i01;
+    o->z[1] = (G[1] * a0) * i01;
+    o->z[2] = (G[2] * denA) * i2A;
+    o->q[0] = (numA * a2) * i2A;
+    o->z[3] = (G[3] * a4) * i34;
+    o->z[4] = (G[4] * a3) * i34;
+    o->q[1] = numB * iB;
+    for (int k = 0; k < 5; ++k) o->zs[k] = o->z[k] * o->z[k];
+    o->qs[0] = o->q[0] * o->q[0];
+    o->qs[1] = o->q[1] * o->q[1];
+    o->a[0] = a0, o->a[1] = a1, o->a[2] = a2, o->a[3] = a3, o->a[4] = a4;
+    o->num[0] = numA, o->num[1] = numB, o->den[0] = denA, o->den[1] = denB;
+}
+
+/* every argument of this pair inside the far tier (and both faces seen from the front) */
+static inline int pair_is_far(const pair_pre *o)
+{
+    for (int k = 0; k < 5; ++k)
+        if (orc_hi(o->zs[k]) >= ORC_HI_FAR) return 0;
+    return orc_hi(o->qs[0]) < ORC_HI_FAR && orc_hi(o->qs[1]) < ORC_HI_FAR && orc_hi(o->den[0]) > 0 &&
+           orc_hi(o->den[1]) > 0;
+}
+
+/* The transcendental part.  `far_row`: every pair of this pair's ROW (32 consecutive records -- what one warp of the
+ * CUDA kernels evaluates together) is far: 4-coefficient polynomials.  Otherwise each term chooses for itself: the
+ * thresholds are doubles whose low word is 0 (0x3FA47AE1'00000000 = 0.04 - 8.3e-9 for z^2, 0x3F847AE1'00000000 =
+ * 0.01 - 2.1e-9 for q^2), so for x >= 0 `x < threshold` is a comparison of the high words (the CUDA side does it on
+ * the integer pipe; a NaN fails it; `den > 0` likewise reads hi(den) > 0): inside -> 7 / 5-coefficient minimax
+ * polynomial; an edge seen under a larger angle takes a division of its own and the ln-based atanh, a face seen under
+ * a larger solid angle (or from behind) the full-range atan2. */
+static inline void pair_finish(const pair_pre *o, int far_row, double *ax, double *ay, double *az, double *pv)
+{
+    const double *rc = o->rc, *NA = rc + 12, *NB = rc + 15, *G = rc + 36;
+    double ln[5], om[2];
+    if (far_row) {
+        for (int k = 0; k < 5; ++k) ln[k] = orc_two_atanh_far(o->z[k], o->zs[k]);
+        for (int f = 0; f < 2; ++f) om[f] = orc_two_atan_far(o->q[f], o->qs[f]);
+    } else {
+        for (int k = 0; k < 5; ++k)
+            ln[k] = (orc_hi(o->zs[k]) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(o->z[k], o->zs[k]) : orc_two_atanh(G[k] / o->a[k]);
+        for (int f = 0; f < 2; ++f) {
+            const int ok = (orc_hi(o->den[f]) > 0) && (orc_hi(o->qs[f]) < ORC_HI_Q2MAX);
+            om[f] = ok ? orc_two_atan_mm(o->q[f], o->qs[f]) : 2.0 * orc_atan2(o->num[f], o->den[f]);
+        }
+    }
+    const double SA = ORC_FMA(-o->hpA, om[0], ORC_FMA(o->hA2, ln[2], ORC_FMA(o->hA1, ln[1], o->hA0 * ln[0])));
+    const double SB = ORC_FMA(-o->hpB, om[1], ORC_FMA(o->hB2, ln[4], ORC_FMA(o->hB1, ln[3], o->hB0 * ln[0])));
     *ax = ORC_FMA(NB[0], SB, ORC_FMA(NA[0], SA, *ax));
     *ay = ORC_FMA(NB[1], SB, ORC_FMA(NA[1], SA, *ay));
     *az = ORC_FMA(NB[2], SB, ORC_FMA(NA[2], SA, *az));
-    *pv = ORC_FMA(hpB, SB, ORC_FMA(hpA, SA, *pv));
+    *pv = ORC_FMA(o->hpB, SB, ORC_FMA(o->hpA, SA, *pv));
 }
 
 /* Sum over pair records in the order of a 32-lane warp: lane l accumulates records l, l+32, ... in increasing
  * order, then an xor-butterfly adds the 32 partial sums (polyhedral_gravity itself reduces with an
- * unspecified parallel order, so any fixed order is as faithful as another). */
+ * unspecified parallel order, so any fixed order is as faithful as another).  The records are taken a ROW of 32 at a
+ * time, as a warp does: the row's tier (far / not) is decided from all of its pairs (the padding records a warp sees
+ * in the last row are far by construction). */
 static void gravity_point(const orc_mesh *m, const double P[3], double acc[3], double *pot)
 {
     double sx[32] = {0.0}, sy[32] = {0.0}, sz[32] = {0.0}, sv[32] = {0.0};
-    for (int i = 0; i < m->n_pairs; ++i)
-        pair_term(m->prec + (size_t)i * PREC, P, &sx[i & 31], &sy[i & 31], &sz[i & 31], &sv[i & 31]);
+    pair_pre pre[32];
+    for (int base = 0; base < m->n_pairs; base += 32) {
+        const int n = m->n_pairs - base < 32 ? m->n_pairs - base : 32;
+        int far_row = 1;
+        for (int i = 0; i < n; ++i) {
+            pair_prelim(m->prec + (size_t)(base + i) * PREC, P, &pre[i]);
+            far_row &= pair_is_far(&pre[i]);
+        }
+        for (int i = 0; i < n; ++i) pair_finish(&pre[i], far_row, &sx[i], &sy[i], &sz[i], &sv[i]);
+    }
     const double ax = orc_butterfly32(sx), ay = orc_butterfly32(sy), az = orc_butterfly32(sz);
     acc[0] = m->Grho * ax;
     acc[1] = m->Grho * ay;

@@ -23,12 +23,18 @@
 // Two faces that share an edge, one field point (pair record of common.cuh): S_A and S_B, the scalars that
 // multiply N_A and N_B.  Shared between the two: the distances to v0 and v1, r0.r1, l0*l1 and the edge term
 // LN_0 of e0; on the common path ONE division serves the five edge quotients and the two solid-angle quotients.
-// kCompact: `scratch` is 96 doubles of shared memory owned by the calling warp, the whole warp is converged on the
-// call, and the out-of-range edge terms of the 32 pairs are compacted across the lanes (below).
-template <bool kCompact = false, class Fld>
+// kMode says how the caller's warp is organised:
+//   kPairLane     every lane has its own field point (thread-per-point kernel): no warp votes;
+//   kPairRow      the warp is converged on the call and its 32 lanes hold one ROW of 32 consecutive pair records for
+//                 ONE field point: the row's tier (far / not) is decided by a vote;
+//   kPairRowSmem  the same, plus `scratch` = 96 doubles of shared memory owned by the warp: the out-of-range edge
+//                 terms of the row are compacted across the lanes (below).
+enum : int { kPairLane = 0, kPairRow = 1, kPairRowSmem = 2 };
+template <int kMode = kPairLane, class Fld>
 __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz, double &SA, double &SB,
                                        double &hpA_out, double &hpB_out, double *scratch = nullptr)
 {
+    constexpr bool kCompact = kMode == kPairRowSmem;
     const double r0x = fld(0) - Px, r0y = fld(1) - Py, r0z = fld(2) - Pz;
     const double r1x = fld(3) - Px, r1y = fld(4) - Py, r1z = fld(5) - Pz;
     const double r2x = fld(6) - Px, r2y = fld(7) - Py, r2z = fld(8) - Pz;
@@ -81,11 +87,28 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
               hz3 = __double2hiint(z3s), hz4 = __double2hiint(z4s);
     const int hqA = __double2hiint(qAs), hqB = __double2hiint(qBs), hdA = __double2hiint(denA),
               hdB = __double2hiint(denB);
-    const bool anybad = (max(max(max(hz0, hz1), hz2), max(hz3, hz4)) >= kHiZ2Max) | (max(hqA, hqB) >= kHiQ2Max) |
-                        (min(hdA, hdB) <= 0);
+    const int hzmax = max(max(max(hz0, hz1), hz2), max(hz3, hz4)), hqmax = max(hqA, hqB), hdmin = min(hdA, hdB);
+    constexpr unsigned kFull = 0xffffffffu;
+    hpA_out = hpA;
+    hpB_out = hpB;
+    if (kMode != kPairLane) {
+        // FAR ROW: every z^2 and q^2 of the 32 pairs below 0x3F647AE1'00000000 (= 0.0025 - 5e-10) and every face seen
+        // from the front -- 84 % (init-like) to 97 % (converged-like) of the rows a population evaluates.  The row
+        // takes 4-coefficient polynomials (17 FP64 instructions less per pair); the tier is a property of (row, field
+        // point), so it does not depend on which warp evaluates the row.  Half values, as below.
+        const bool lane_far = (max(hzmax, hqmax) < kHiFar) & (hdmin > 0);
+        if (__all_sync(kFull, lane_far)) {
+            const double f0 = tm_atanh_far(z0, z0s), f1 = tm_atanh_far(z1, z1s), f2 = tm_atanh_far(z2, z2s),
+                         f3 = tm_atanh_far(z3, z3s), f4 = tm_atanh_far(z4, z4s);
+            const double wA = tm_atan_far(qA, qAs), wB = tm_atan_far(qB, qBs);
+            SA = fma(-hpA, wA, fma(hA2, f2, fma(hA1, f1, hA0 * f0)));
+            SB = fma(-hpB, wB, fma(hB2, f4, fma(hB1, f3, hB0 * f0)));
+            return;
+        }
+    }
+    const bool anybad = (hzmax >= kHiZ2Max) | (hqmax >= kHiQ2Max) | (hdmin <= 0);
     // the warp vote is issued BEFORE the polynomials so that its latency (integer maxima -> compare -> vote) hides
     // behind them instead of sitting at the end of the row with nothing left to issue
-    constexpr unsigned kFull = 0xffffffffu;
     const bool warp_bad = kCompact ? (__any_sync(kFull, anybad) != 0) : false;
     // HALF values from here on: atanh(z) and atan(q) instead of 2 atanh(z) = LN and 2 atan(q) = omega.  Scaling by
     // 2 is exact, so S/2 and the accumulated sum/2 carry the same bits; the callers multiply by 2 G rho at the end.
@@ -152,19 +175,17 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
         if (isA) omA = v;
         else omB = v;
     }
-    hpA_out = hpA;
-    hpB_out = hpB;
     SA = fma(-hpA, omA, fma(hA2, ln2, fma(hA1, ln1, hA0 * ln0)));
     SB = fma(-hpB, omB, fma(hB2, ln4, fma(hB1, ln3, hB0 * ln0)));
 }
 
 // acc += (N_A S_A + N_B S_B) / 2 (and pot += (hp_A S_A + hp_B S_B) / 2): pair_S works in exact halves
-template <bool kPot, bool kCompact = false, class Fld>
+template <bool kPot, int kMode = kPairLane, class Fld>
 __device__ __forceinline__ void pair_term(Fld fld, double Px, double Py, double Pz, double &ax, double &ay,
                                           double &az, double &pot, double *scratch = nullptr)
 {
     double SA, SB, hpA, hpB;
-    pair_S<kCompact>(fld, Px, Py, Pz, SA, SB, hpA, hpB, scratch);
+    pair_S<kMode>(fld, Px, Py, Pz, SA, SB, hpA, hpB, scratch);
     ax = fma(fld(15), SB, fma(fld(12), SA, ax));
     ay = fma(fld(16), SB, fma(fld(13), SA, ay));
     az = fma(fld(17), SB, fma(fld(14), SA, az));

@@ -92,7 +92,7 @@ __device__ __forceinline__ void warp_gravity_global(const double *__restrict__ s
     ax = ay = az = pv = 0.0;
     for (int f = lane; f < Ppad32; f += 32) {
         const PairCols<true> cols{reinterpret_cast<const double2 *>(soa) + f, Ppad32};
-        pair_term<true>(cols, Px, Py, Pz, ax, ay, az, pv);
+        pair_term<true, kPairRow>(cols, Px, Py, Pz, ax, ay, az, pv);
     }
     ax = warp_sum(ax);
     ay = warp_sum(ay);

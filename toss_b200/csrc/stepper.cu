@@ -96,9 +96,9 @@ __device__ __forceinline__ void refill_if_released(uint64_t *bars, int *claim, d
 // arithmetic, and therefore every result bit, is the same for any team size.
 enum : int { kModeGrav = 0, kModeSkip = 1, kModeRetire = 2 };
 #ifdef K2_NO_COMPACT
-constexpr bool kCompactRows = false;   // developer A/B: per-lane loops over the out-of-range terms
+constexpr int kCompactRows = kPairRow;       // developer A/B: per-lane loops over the out-of-range terms
 #else
-constexpr bool kCompactRows = true;
+constexpr int kCompactRows = kPairRowSmem;
 #endif
 constexpr int kScratchDoubles = 96;             // pair_S scratch per warp: |G|[32] | l1+l2[32] | value[32]
 #ifdef K2_NO_TEAMBUF
