@@ -60,6 +60,8 @@ struct StepArgs {
     double *knots_t, *knots_y, *knots_f, *intervals;
     int32_t *seg_start, *n_seg, *collision, *queue;
     const int32_t *order;      // queue position -> trajectory index (longest predicted first), or NULL
+    int first_round, first_extra;   // static first round: every CTA takes first_round queue positions, the first
+                                    // first_extra CTAs one more (see the fetch)
     int proxy_n;               // PROXY instantiation: number of mascons (pair_soa then points at [n][4] x y z G*m)
     double proxy_soft2;
     int32_t *proxy_cost;       // PROXY: predicted RHS count per trajectory
@@ -258,18 +260,22 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     for (;;) {
         // ------------------------------------------------ fetch a trajectory, decode the chromosome
         if (!active && !queue_empty) {
-            // The first trajectory of every team is assigned statically, team t of CTA b takes queue position
-            // b + gridDim.x * t: a population smaller than the machine spreads over ALL SMs (a warp that shares its
-            // scheduler with fewer warps runs faster) instead of filling the first CTAs; later ones come from the
-            // atomic cursor, which starts behind the static round.
+            // The first round is assigned statically: CTA b takes k (or k + 1) consecutive queue positions, k =
+            // floor(pop / CTAs) capped by the teams of a CTA.  A population smaller than the machine spreads over ALL
+            // SMs (a warp that shares its scheduler with fewer warps runs faster) instead of filling the first CTAs;
+            // a large one hands every CTA a contiguous block of the longest-first order, so trajectories of similar
+            // length -- the long ones are the ones that pass close to the body and take the slow rows -- share a tile
+            // ring.  Later trajectories come from the atomic cursor, which starts behind the static round.
             int nxt = 0;
-            if (first_fetch) {
-                nxt = (int)blockIdx.x + (int)gridDim.x * team;
-                first_fetch = false;
+            const int b = (int)blockIdx.x;
+            const int mine = a.first_round + (b < a.first_extra ? 1 : 0);   // static positions of this CTA
+            if (first_fetch && team < mine) {
+                nxt = b * a.first_round + (b < a.first_extra ? b : a.first_extra) + team;
             } else {
-                if (lane == 0) nxt = atomicAdd(a.queue, 1) + (int)gridDim.x * (kK2Warps / kTeam);
+                if (lane == 0) nxt = atomicAdd(a.queue, 1) + (int)gridDim.x * a.first_round + a.first_extra;
                 nxt = __shfl_sync(0xffffffffu, nxt, 0);
             }
+            first_fetch = false;
             if (nxt >= a.pop) {
                 queue_empty = true;
             } else {
@@ -823,6 +829,8 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
                              kK2BarSlots * 8 + (size_t)kTeamBufs * kTeamBufDoubles * 8 +
                              (size_t)kK2Warps * kScratchDoubles * 8;
         const int pctas = pop < K2_MINBLOCKS * ctx->sm_count ? pop : K2_MINBLOCKS * ctx->sm_count;
+        px.first_round = pop / pctas < kK2Warps ? pop / pctas : kK2Warps;
+        px.first_extra = pop / pctas < kK2Warps ? pop % pctas : 0;
         TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)psmem));
         stepper_kernel<false, 1, true><<<pctas, kK2Threads, psmem, st>>>(px);
@@ -840,6 +848,10 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     // one CTA per SM as soon as there is a trajectory for it (the static first round spreads them over the CTAs)
     const int max_ctas = K2_MINBLOCKS * ctx->sm_count;
     const int ctas = pop < max_ctas ? pop : max_ctas;
+    a.first_round = pop / ctas < kK2Warps / team ? pop / ctas : kK2Warps / team;
+    a.first_extra = pop / ctas < kK2Warps / team ? pop % ctas : 0;
+    if (const char *e = getenv("TOSS_B200_FIRST_ROUND"))   // developer A/B: 1 = one static position per CTA
+        if (atoi(e) == 1) a.first_round = 1, a.first_extra = 0;
     const size_t smem = resident ? resident_bytes : stream_bytes;
 #define TOSS_LAUNCH_STEPPER(STREAM, TEAM)                                                                          \
     do {                                                                                                           \
