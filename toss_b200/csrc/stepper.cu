@@ -794,11 +794,13 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     a.queue = reinterpret_cast<int32_t *>(ws + L.queue);
     a.counters = reinterpret_cast<toss_counters *>(ws + L.counters);
     TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
-    // warps per trajectory: one when the population fills the machine several times over; two or four below that,
-    // which shortens the tail (trajectory lengths spread 4x) and fills the SMs of small populations.  Results do
-    // not depend on it.
+    // warps per trajectory: one when every warp of the machine gets a trajectory; two or four below that, which fills
+    // the SMs of small populations and shortens their longest trajectory.  Results do not depend on it.
     const int slots = K2_MINBLOCKS * ctx->sm_count * kK2Warps;
-    int team = pop >= 6 * slots ? 1 : (2 * pop >= 3 * slots ? 2 : 4);
+    // Measured (lp / full mesh, pop 1024 .. 8192, longest-first queue): the best team size keeps the machine loaded
+    // with one to two waves of teams -- 4 warps up to slots/2 trajectories, 2 up to slots, 1 beyond (a team of two
+    // runs a trajectory 1.86x faster, not 2x, so once every warp has a trajectory of its own teams only cost).
+    int team = 4 * (long long)pop <= 2LL * slots ? 4 : (2 * (long long)pop <= 2LL * slots ? 2 : 1);
     // a team splits the 32-pair ROWS of the table: more warps than rows only adds barrier hand-shakes (lllp: 1 row)
     const int rows = ctx->Ppad32 / 32;
     if (rows < 2) team = 1;
