@@ -49,6 +49,14 @@ static inline double orc_two_atanh_far(double z, double z2)
     const double zz = z + z;
     return ORC_FMA(zz * z2, p, zz);
 }
+/* middle tier: 5 coefficients for z*z <= 0.01005 (approximation error 4.6e-17 of the value) */
+static inline double orc_two_atanh_mid(double z, double z2)
+{
+    double p = ORC_ATANH_MID[4];
+    for (int k = 3; k >= 0; --k) p = ORC_FMA(p, z2, ORC_ATANH_MID[k]);
+    const double zz = z + z;
+    return ORC_FMA(zz * z2, p, zz);
+}
 static inline double orc_two_atan_far(double t, double t2)
 {
     double p = ORC_ATAN_FAR[3];

@@ -423,29 +423,35 @@ static inline void pair_prelim(const double *rc, const double P[3], pair_pre *o)
     o->num[0] = numA, o->num[1] = numB, o->den[0] = denA, o->den[1] = denB;
 }
 
-/* every argument of this pair inside the far tier (and both faces seen from the front) */
-static inline int pair_is_far(const pair_pre *o)
+/* Tier of a pair: 2 = far (every z^2 and q^2 below 0x3F647AE1'00000000 = 0.0025 - 5e-10, both faces seen from the
+ * front), 1 = middle (every z^2 and q^2 below 0x3F847AE1'00000000 = 0.01 - 2.1e-9, faces from the front), 0 = neither. */
+static inline int pair_tier(const pair_pre *o)
 {
+    int32_t h = orc_hi(o->qs[0]) > orc_hi(o->qs[1]) ? orc_hi(o->qs[0]) : orc_hi(o->qs[1]);
     for (int k = 0; k < 5; ++k)
-        if (orc_hi(o->zs[k]) >= ORC_HI_FAR) return 0;
-    return orc_hi(o->qs[0]) < ORC_HI_FAR && orc_hi(o->qs[1]) < ORC_HI_FAR && orc_hi(o->den[0]) > 0 &&
-           orc_hi(o->den[1]) > 0;
+        if (orc_hi(o->zs[k]) > h) h = orc_hi(o->zs[k]);
+    if (!(orc_hi(o->den[0]) > 0 && orc_hi(o->den[1]) > 0)) return 0;
+    return h < ORC_HI_FAR ? 2 : (h < ORC_HI_Q2MAX ? 1 : 0);
 }
 
-/* The transcendental part.  `far_row`: every pair of this pair's ROW (32 consecutive records -- what one warp of the
- * CUDA kernels evaluates together) is far: 4-coefficient polynomials.  Otherwise each term chooses for itself: the
+/* The transcendental part.  `row_tier` = the lowest tier among the pairs of this pair's ROW (32 consecutive records --
+ * what one warp of the CUDA kernels evaluates together): 2 -> 4-coefficient polynomials, 1 -> 5-coefficient atanh and
+ * the 5-coefficient atan.  Otherwise each term chooses for itself: the
  * thresholds are doubles whose low word is 0 (0x3FA47AE1'00000000 = 0.04 - 8.3e-9 for z^2, 0x3F847AE1'00000000 =
  * 0.01 - 2.1e-9 for q^2), so for x >= 0 `x < threshold` is a comparison of the high words (the CUDA side does it on
  * the integer pipe; a NaN fails it; `den > 0` likewise reads hi(den) > 0): inside -> 7 / 5-coefficient minimax
  * polynomial; an edge seen under a larger angle takes a division of its own and the ln-based atanh, a face seen under
  * a larger solid angle (or from behind) the full-range atan2. */
-static inline void pair_finish(const pair_pre *o, int far_row, double *ax, double *ay, double *az, double *pv)
+static inline void pair_finish(const pair_pre *o, int row_tier, double *ax, double *ay, double *az, double *pv)
 {
     const double *rc = o->rc, *NA = rc + 12, *NB = rc + 15, *G = rc + 36;
     double ln[5], om[2];
-    if (far_row) {
+    if (row_tier == 2) {
         for (int k = 0; k < 5; ++k) ln[k] = orc_two_atanh_far(o->z[k], o->zs[k]);
         for (int f = 0; f < 2; ++f) om[f] = orc_two_atan_far(o->q[f], o->qs[f]);
+    } else if (row_tier == 1) {
+        for (int k = 0; k < 5; ++k) ln[k] = orc_two_atanh_mid(o->z[k], o->zs[k]);
+        for (int f = 0; f < 2; ++f) om[f] = orc_two_atan_mm(o->q[f], o->qs[f]);
     } else {
         for (int k = 0; k < 5; ++k)
             ln[k] = (orc_hi(o->zs[k]) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(o->z[k], o->zs[k]) : orc_two_atanh(G[k] / o->a[k]);
@@ -465,20 +471,21 @@ static inline void pair_finish(const pair_pre *o, int far_row, double *ax, doubl
 /* Sum over pair records in the order of a 32-lane warp: lane l accumulates records l, l+32, ... in increasing
  * order, then an xor-butterfly adds the 32 partial sums (polyhedral_gravity itself reduces with an
  * unspecified parallel order, so any fixed order is as faithful as another).  The records are taken a ROW of 32 at a
- * time, as a warp does: the row's tier (far / not) is decided from all of its pairs (the padding records a warp sees
- * in the last row are far by construction). */
+ * time, as a warp does: the row's tier (far / middle / neither) is decided from all of its pairs (the padding records
+ * a warp sees in the last row are far by construction). */
 static void gravity_point(const orc_mesh *m, const double P[3], double acc[3], double *pot)
 {
     double sx[32] = {0.0}, sy[32] = {0.0}, sz[32] = {0.0}, sv[32] = {0.0};
     pair_pre pre[32];
     for (int base = 0; base < m->n_pairs; base += 32) {
         const int n = m->n_pairs - base < 32 ? m->n_pairs - base : 32;
-        int far_row = 1;
+        int row_tier = 2;
         for (int i = 0; i < n; ++i) {
             pair_prelim(m->prec + (size_t)(base + i) * PREC, P, &pre[i]);
-            far_row &= pair_is_far(&pre[i]);
+            const int t = pair_tier(&pre[i]);
+            if (t < row_tier) row_tier = t;
         }
-        for (int i = 0; i < n; ++i) pair_finish(&pre[i], far_row, &sx[i], &sy[i], &sz[i], &sv[i]);
+        for (int i = 0; i < n; ++i) pair_finish(&pre[i], row_tier, &sx[i], &sy[i], &sz[i], &sv[i]);
     }
     const double ax = orc_butterfly32(sx), ay = orc_butterfly32(sy), az = orc_butterfly32(sz);
     acc[0] = m->Grho * ax;

@@ -14,6 +14,8 @@ range each call site guarantees (see tmath.cuh / orc_math.h):
       sum; their approximation error (1.6e-17, 4.2e-17 of the function value) is below the rounding error
   ATANH_FAR[k], ATAN_FAR[k], k = 0..3: the same on u <= 0.0025 (errors 2.0e-17, 2.0e-17) -- rows of 32 pairs whose
       every argument is that small (84 % .. 97 % of the rows a trajectory population evaluates)
+  ATANH_MID[k], k = 0..4: the same on u <= 0.01005 (error 4.6e-17) -- rows whose every z^2 is below 0.01 (another 12 %
+      of the rows of an init-like population)
   SIN[k]   = (-1)^(k+1)/(2k+3)!,  k = 0..8    sin(r) = r + r^3 sum SIN[k] r^(2k),          |r| <= pi/4
   COS[k]   = (-1)^(k+1)/(2k+2)!,  k = 0..8    cos(r) = 1 + r^2 sum COS[k] r^(2k)
 """
@@ -110,6 +112,7 @@ TABLES = {
     "ATAN_MM": remez(g_atan, "0.01005", 5),
     "ATANH_FAR": remez(g_atanh, "0.0025", 4),
     "ATAN_FAR": remez(g_atan, "0.0025", 4),
+    "ATANH_MID": remez(g_atanh, "0.01005", 5),
     "ATANH": [dbl(Fr(1, 2 * k + 3)) for k in range(11)],
     "ATAN": [dbl(Fr((-1) ** (k + 1), 2 * k + 3)) for k in range(22)],
     "SIN": [dbl(Fr((-1) ** (k + 1), factorial(2 * k + 3))) for k in range(9)],
