@@ -20,6 +20,10 @@ for v in "$@"; do
     nocompact) build nocompact -DK2_NO_COMPACT ;;
     w8x2s2) build w8x2s2 -DK2_WARPS=8 -DK2_MINBLOCKS=2 -DK2_STAGES=2 -DK2_NO_TEAMBUF ;;
     s4nt)   build s4nt -DK2_STAGES=4 -DK2_NO_TEAMBUF ;;
+    k1mb5)  build k1mb5 -DK1_MINBLOCKS=5 ;;
+    k1mb6)  build k1mb6 -DK1_MINBLOCKS=6 ;;
+    k1mb3u2) build k1mb3u2 -DK1_MINBLOCKS=3 -DK1_UNROLL=2 ;;
+    k1mb4u2) build k1mb4u2 -DK1_MINBLOCKS=4 -DK1_UNROLL=2 ;;
     prof)   build prof -DK2_PROFILE ;;
     prof4)  build prof4 -DK2_PROFILE -DK2_STAGES=4 ;;
     *) echo "unknown variant $v"; exit 1 ;;

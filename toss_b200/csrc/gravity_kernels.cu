@@ -13,8 +13,16 @@ constexpr int kK1Threads = 128;
 constexpr int kK1Stages = 4;
 constexpr int kPairTileBytes = kPairAosTile * kPairAosStride * 8;
 
+#ifndef K1_MINBLOCKS
+#define K1_MINBLOCKS 4
+#endif
+#ifndef K1_UNROLL
+#define K1_UNROLL 1
+#endif
+constexpr int kK1Unroll = K1_UNROLL;
+
 template <bool kPot>
-__global__ void __launch_bounds__(kK1Threads, 4)
+__global__ void __launch_bounds__(kK1Threads, K1_MINBLOCKS)
 gravity_points_kernel(const double *__restrict__ pair_aos, int n_tiles, int last_tile_pairs,
                            const double *__restrict__ pts, int64_t n,
                            double *__restrict__ acc, double *__restrict__ pot, double Grho)
@@ -63,7 +71,7 @@ gravity_points_kernel(const double *__restrict__ pair_aos, int n_tiles, int last
         mbar_wait(&full[s], ph);
         const double *tile = tiles + (size_t)s * kTileDoubles;
         const int p_end = (it == n_tiles - 1) ? last_tile_pairs : kPairAosTile;
-#pragma unroll 1
+#pragma unroll kK1Unroll
         for (int f = 0; f < p_end; ++f) {
             const double *rec = tile + f * kPairAosStride;
             pair_term<kPot>([rec](int k) { return rec[k]; }, Px, Py, Pz, ax, ay, az, pv);
