@@ -354,7 +354,7 @@ static void gravity_point_direct(const orc_mesh *m, const double P[3], double ac
  * The seven quotients share ONE division and atanh / atan are short odd minimax polynomials; a term whose
  * argument is out of the polynomial's range (an edge or a face close to the field point) falls back, on its own,
  * to a division of its own + ln-based atanh, or to the full-range atan2. */
-#define ORC_HI_Z2MAX 0x3FA47AE1
+#define ORC_HI_Z2MAX 0x3FC47AE1 /* high word of 0.16: z^2 < 0x3FC47AE1'00000000 = 0.16 - 3.3e-8 */
 #define ORC_HI_Q2MAX 0x3F847AE1
 #define ORC_HI_FAR 0x3F647AE1 /* high word of 0.0025: z^2, q^2 < 0x3F647AE1'00000000 = 0.0025 - 5.2e-10 */
 static inline int32_t orc_hi(double x)   /* high word of the IEEE-754 pattern, as a signed integer */
@@ -437,9 +437,9 @@ static inline int pair_tier(const pair_pre *o)
 /* The transcendental part.  `row_tier` = the lowest tier among the pairs of this pair's ROW (32 consecutive records --
  * what one warp of the CUDA kernels evaluates together): 2 -> 4-coefficient polynomials, 1 -> 5-coefficient atanh and
  * the 5-coefficient atan.  Otherwise each term chooses for itself: the
- * thresholds are doubles whose low word is 0 (0x3FA47AE1'00000000 = 0.04 - 8.3e-9 for z^2, 0x3F847AE1'00000000 =
+ * thresholds are doubles whose low word is 0 (0x3FC47AE1'00000000 = 0.16 - 3.3e-8 for z^2, 0x3F847AE1'00000000 =
  * 0.01 - 2.1e-9 for q^2), so for x >= 0 `x < threshold` is a comparison of the high words (the CUDA side does it on
- * the integer pipe; a NaN fails it; `den > 0` likewise reads hi(den) > 0): inside -> 7 / 5-coefficient minimax
+ * the integer pipe; a NaN fails it; `den > 0` likewise reads hi(den) > 0): inside -> 11 / 5-coefficient minimax
  * polynomial; an edge seen under a larger angle takes a division of its own and the ln-based atanh, a face seen under
  * a larger solid angle (or from behind) the full-range atan2. */
 static inline void pair_finish(const pair_pre *o, int row_tier, double *ax, double *ay, double *az, double *pv)
@@ -454,7 +454,7 @@ static inline void pair_finish(const pair_pre *o, int row_tier, double *ax, doub
         for (int f = 0; f < 2; ++f) om[f] = orc_two_atan_mm(o->q[f], o->qs[f]);
     } else {
         for (int k = 0; k < 5; ++k)
-            ln[k] = (orc_hi(o->zs[k]) < ORC_HI_Z2MAX) ? orc_two_atanh_mm(o->z[k], o->zs[k]) : orc_two_atanh(G[k] / o->a[k]);
+            ln[k] = (orc_hi(o->zs[k]) < ORC_HI_Z2MAX) ? orc_two_atanh_wide(o->z[k], o->zs[k]) : orc_two_atanh(G[k] / o->a[k]);
         for (int f = 0; f < 2; ++f) {
             const int ok = (orc_hi(o->den[f]) > 0) && (orc_hi(o->qs[f]) < ORC_HI_Q2MAX);
             om[f] = ok ? orc_two_atan_mm(o->q[f], o->qs[f]) : 2.0 * orc_atan2(o->num[f], o->den[f]);

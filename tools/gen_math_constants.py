@@ -16,6 +16,8 @@ range each call site guarantees (see tmath.cuh / orc_math.h):
       every argument is that small (84 % .. 97 % of the rows a trajectory population evaluates)
   ATANH_MID[k], k = 0..4: the same on u <= 0.01005 (error 4.6e-17) -- rows whose every z^2 is below 0.01 (another 12 %
       of the rows of an init-like population)
+  ATANH_WIDE[k], k = 0..10: the same on u <= 0.1601 (error 4.0e-18) -- the remaining rows of the lane-per-pair kernels:
+      the wider range leaves a third as many rows with terms that need the ln-based evaluation
   SIN[k]   = (-1)^(k+1)/(2k+3)!,  k = 0..8    sin(r) = r + r^3 sum SIN[k] r^(2k),          |r| <= pi/4
   COS[k]   = (-1)^(k+1)/(2k+2)!,  k = 0..8    cos(r) = 1 + r^2 sum COS[k] r^(2k)
 """
@@ -113,6 +115,7 @@ TABLES = {
     "ATANH_FAR": remez(g_atanh, "0.0025", 4),
     "ATAN_FAR": remez(g_atan, "0.0025", 4),
     "ATANH_MID": remez(g_atanh, "0.01005", 5),
+    "ATANH_WIDE": remez(g_atanh, "0.1601", 11),
     "ATANH": [dbl(Fr(1, 2 * k + 3)) for k in range(11)],
     "ATAN": [dbl(Fr((-1) ** (k + 1), 2 * k + 3)) for k in range(22)],
     "SIN": [dbl(Fr((-1) ** (k + 1), factorial(2 * k + 3))) for k in range(9)],

@@ -6,10 +6,11 @@ sys.path.insert(0, str(ROOT))
 import numpy as np, torch
 from toss_b200 import _native as N
 from oracle import oracle as O
-from bench import init_like_population, FIXED_POS
+from bench import init_like_population, converged_like_population, FIXED_POS
 c = N.Context(0); v, f = O.load_mesh("lp"); c.upload_mesh(v, f, 533.0); c.upload_grid(*O.default_grid())
 p = N.make_params(stop_on_collision=1); pop = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
-xs = torch.from_numpy(init_like_population(pop, 2, 1005)).cuda()
+kind = sys.argv[3] if len(sys.argv) > 3 else 'init'
+xs = torch.from_numpy((init_like_population if kind == 'init' else converged_like_population)(pop, 2, 1005)).cuda()
 c.integrate(p, xs, FIXED_POS, 2, 1024); torch.cuda.synchronize()
 pr = c.integrate(p, xs, FIXED_POS, 2, 1024); torch.cuda.synchronize()
 q = pr.ws[pr.L.queue + 16:pr.L.queue + 64].view(torch.int64).cpu().numpy()

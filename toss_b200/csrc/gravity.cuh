@@ -119,17 +119,24 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
             return;
         }
     }
-    const bool anybad = (hzmax >= kHiZ2Max) | (hqmax >= kHiQ2Max) | (hdmin <= 0);
+    // the rows that are left: the lane-per-pair kernels take an 11-coefficient atanh up to z^2 < 0.16 (a third as many
+    // rows with out-of-range edge terms as with the 7-coefficient one up to 0.04; the extra 20 FP64 instructions fall
+    // on the 5 % of the rows that get here); the thread-per-point kernel keeps 7 coefficients up to 0.04
+    constexpr int kZ2Max = kMode == kPairLane ? kHiZ2Max : kHiZ2Wide;
+    const bool anybad = (hzmax >= kZ2Max) | (hqmax >= kHiQ2Max) | (hdmin <= 0);
     // the warp vote is issued BEFORE the polynomials so that its latency (integer maxima -> compare -> vote) hides
     // behind them instead of sitting at the end of the row with nothing left to issue
     const bool warp_bad = kCompact ? (__any_sync(kFull, anybad) != 0) : false;
     // HALF values from here on: atanh(z) and atan(q) instead of 2 atanh(z) = LN and 2 atan(q) = omega.  Scaling by
     // 2 is exact, so S/2 and the accumulated sum/2 carry the same bits; the callers multiply by 2 G rho at the end.
-    double ln0 = tm_atanh_mm(z0, z0s);
-    double ln1 = tm_atanh_mm(z1, z1s);
-    double ln2 = tm_atanh_mm(z2, z2s);
-    double ln3 = tm_atanh_mm(z3, z3s);
-    double ln4 = tm_atanh_mm(z4, z4s);
+    double ln0, ln1, ln2, ln3, ln4;
+    if (kMode == kPairLane) {
+        ln0 = tm_atanh_mm(z0, z0s), ln1 = tm_atanh_mm(z1, z1s), ln2 = tm_atanh_mm(z2, z2s), ln3 = tm_atanh_mm(z3, z3s),
+        ln4 = tm_atanh_mm(z4, z4s);
+    } else {
+        ln0 = tm_atanh_wide(z0, z0s), ln1 = tm_atanh_wide(z1, z1s), ln2 = tm_atanh_wide(z2, z2s),
+        ln3 = tm_atanh_wide(z3, z3s), ln4 = tm_atanh_wide(z4, z4s);
+    }
     double omA = tm_atan_mm(qA, qAs);
     double omB = tm_atan_mm(qB, qBs);
     unsigned badw = 0u;
@@ -142,8 +149,8 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
         // max-over-lanes(#terms of a lane).  Same operations on the same operands: the values do not depend on who
         // computes them.
         if (warp_bad) {
-            const unsigned bad = (hz0 < kHiZ2Max ? 0u : 1u) | (hz1 < kHiZ2Max ? 0u : 2u) | (hz2 < kHiZ2Max ? 0u : 4u) |
-                                 (hz3 < kHiZ2Max ? 0u : 8u) | (hz4 < kHiZ2Max ? 0u : 16u);
+            const unsigned bad = (hz0 < kZ2Max ? 0u : 1u) | (hz1 < kZ2Max ? 0u : 2u) | (hz2 < kZ2Max ? 0u : 4u) |
+                                 (hz3 < kZ2Max ? 0u : 8u) | (hz4 < kZ2Max ? 0u : 16u);
             badw = ((hdA > 0 && hqA < kHiQ2Max) ? 0u : 1u) | ((hdB > 0 && hqB < kHiQ2Max) ? 0u : 2u);
             const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
             const unsigned b0 = __ballot_sync(kFull, bad & 1u), b1 = __ballot_sync(kFull, bad & 2u),
@@ -174,11 +181,11 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
     } else if (anybad) {
         // callers without a converged warp (thread-per-point kernel: 32 different field points): every lane fixes
         // its own terms
-        if (hz0 >= kHiZ2Max) ln0 = 0.5 * tm_two_atanh(tm_div(G0, a0));
-        if (hz1 >= kHiZ2Max) ln1 = 0.5 * tm_two_atanh(tm_div(G1, a1));
-        if (hz2 >= kHiZ2Max) ln2 = 0.5 * tm_two_atanh(tm_div(G2, a2));
-        if (hz3 >= kHiZ2Max) ln3 = 0.5 * tm_two_atanh(tm_div(G3, a3));
-        if (hz4 >= kHiZ2Max) ln4 = 0.5 * tm_two_atanh(tm_div(G4, a4));
+        if (hz0 >= kZ2Max) ln0 = 0.5 * tm_two_atanh(tm_div(G0, a0));
+        if (hz1 >= kZ2Max) ln1 = 0.5 * tm_two_atanh(tm_div(G1, a1));
+        if (hz2 >= kZ2Max) ln2 = 0.5 * tm_two_atanh(tm_div(G2, a2));
+        if (hz3 >= kZ2Max) ln3 = 0.5 * tm_two_atanh(tm_div(G3, a3));
+        if (hz4 >= kZ2Max) ln4 = 0.5 * tm_two_atanh(tm_div(G4, a4));
         badw = ((hdA > 0 && hqA < kHiQ2Max) ? 0u : 1u) | ((hdB > 0 && hqB < kHiQ2Max) ? 0u : 2u);
     }
     while (badw) {   // solid-angle terms out of range: 0.4 per row that has any bad term -- not worth compacting
