@@ -316,7 +316,7 @@ def run_ours(args):
                          "algorithmic_flops_per_launch": alg_flops_per_launch, "kernel_ms": kernel_ms,
                          "traffic": 17.6e3 * (hi - lo),
                          "traffic_note": "DRAM bytes per launch = 17.6 KB per trajectory (the knots), from the ncu capture "
-                                         "profiles/r1i_stepper_ncu_details.csv (28.9 MB read + 260.1 MB written at 16384 "
+                                         "profiles/r1k_stepper_ncu_details.csv (28.3 MB read + 260.9 MB written at 16384 "
                                          "trajectories); the mesh is L2 / shared-memory resident -- the bound is the FP64 "
                                          "pipe's issue rate, not HBM",
                          "note": f"algorithmic = gravity evaluations x {F} faces x {W_FACE} ops (SURVEY.md 8d)"},
