@@ -189,7 +189,8 @@ int toss_measure_fp64_peak(toss_ctx *ctx, double *tflops_out);
 
 /* Test hooks of the arithmetic specification (toss_b200/csrc/tmath.cuh): evaluates elementary function `fn`
  * (0 two_atanh, 1 log, 2 atan2(a,b), 3 sincos -> (out,out2), 4 x^(1/8), 5 x^(1/4), 6 8-term atan series,
- * 7 a/b, 8 sqrt, 9 2 atanh minimax polynomial, 10 2 atan minimax polynomial) over n device values; and counts, over `samples` pseudo-random operands, how often the
+ * 7 a/b, 8 sqrt, 9 2 atanh minimax polynomial, 10 2 atan minimax polynomial, 11 / 12 far-tier 2 atanh / 2 atan,
+ * 13 middle-tier 2 atanh, 14 wide 2 atanh) over n device values; and counts, over `samples` pseudo-random operands, how often the
  * guard-free division / square root differ from the IEEE-rounded intrinsics (must be 0). */
 int toss_math_probe(toss_ctx *ctx, int fn, const double *d_a, const double *d_b, int64_t n, double *d_out,
                     double *d_out2, uintptr_t stream);

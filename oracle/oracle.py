@@ -232,7 +232,7 @@ def gravity_direct(mesh: Mesh, pts):
 
 
 MATH_FN = dict(two_atanh=0, log=1, atan2=2, sincos=3, root8=4, root4=5, atan_series8=6, div=7, sqrt=8,
-               two_atanh_mm=9, two_atan_mm=10)
+               two_atanh_mm=9, two_atan_mm=10, two_atanh_far=11, two_atan_far=12, two_atanh_mid=13, two_atanh_wide=14)
 
 
 def math_probe(fn: str, a, b=None):

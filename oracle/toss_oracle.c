@@ -1118,7 +1118,7 @@ void orc_population_fitness(const orc_mesh *m, const orc_params *p, const double
 
 /* elementary functions of orc_math.h, exposed for tests/test_oracle_math.py and the GPU bit-parity tests.
  * fn: 0 two_atanh(a) 1 log(a) 2 atan2(a,b) 3 sincos(a)->(out,out2) 4 root8(a) 5 root4(a) 6 atan_series8(a)
- *     7 a/b 8 sqrt(a) */
+ *     7 a/b 8 sqrt(a) 9 / 10 minimax 2 atanh / 2 atan of the common path 11 / 12 far tier 13 middle tier 14 wide 2 atanh */
 void orc_math_probe(int fn, const double *a, const double *b, int64_t n, double *out, double *out2)
 {
     for (int64_t i = 0; i < n; ++i) {
@@ -1134,6 +1134,10 @@ void orc_math_probe(int fn, const double *a, const double *b, int64_t n, double 
         case 8: out[i] = sqrt(a[i]); break;
         case 9: out[i] = orc_two_atanh_mm(a[i], a[i] * a[i]); break;
         case 10: out[i] = orc_two_atan_mm(a[i], a[i] * a[i]); break;
+        case 11: out[i] = orc_two_atanh_far(a[i], a[i] * a[i]); break;
+        case 12: out[i] = orc_two_atan_far(a[i], a[i] * a[i]); break;
+        case 13: out[i] = orc_two_atanh_mid(a[i], a[i] * a[i]); break;
+        case 14: out[i] = orc_two_atanh_wide(a[i], a[i] * a[i]); break;
         default: out[i] = NAN;
         }
     }

@@ -36,6 +36,10 @@ def _fn_inputs():
         "sqrt": (10.0 ** rng.uniform(-20, 60, n), None),
         "two_atanh_mm": (np.concatenate([rng.uniform(-0.2, 0.2, n), 10.0 ** rng.uniform(-9, -1, n)]), None),
         "two_atan_mm": (np.concatenate([rng.uniform(-0.1, 0.1, n), 10.0 ** rng.uniform(-9, -1, n)]), None),
+        "two_atanh_far": (np.concatenate([rng.uniform(-0.05, 0.05, n), 10.0 ** rng.uniform(-9, -2, n)]), None),
+        "two_atan_far": (np.concatenate([rng.uniform(-0.05, 0.05, n), 10.0 ** rng.uniform(-9, -2, n)]), None),
+        "two_atanh_mid": (np.concatenate([rng.uniform(-0.1, 0.1, n), 10.0 ** rng.uniform(-9, -1, n)]), None),
+        "two_atanh_wide": (np.concatenate([rng.uniform(-0.4, 0.4, n), 10.0 ** rng.uniform(-9, -1, n)]), None),
     }
 
 

@@ -161,3 +161,33 @@ def test_baseline_config_shapes_at_test_size():
         p, po = both_params(final_time=ft, number_of_spacecrafts=nsc)
         xs = random_population(pop, n_man, 900 + pop, ft)
         _same(c.population_fitness(p, xs, FIXED_POS, n_man), O.population_fitness(m, po, O.default_grid(), xs, FIXED_POS, n_man))
+
+
+@pytest.mark.parametrize("mesh_name,pop,n_spot", [("lp", 32768, 6), ("full", 4096, 2)])
+def test_full_size_populations_through_size_independent_properties(mesh_name, pop, n_spot):
+    """BASELINE configs[4] (lp, pop 32768) and configs[3] (full mesh, pop 4096) at FULL size, 7-day window, where the
+    oracle cannot follow the whole population: (1) a trajectory does not depend on its population -- a random subset
+    evaluated on its own gives the same bits (other team size, other queue order, other CTA neighbours); (2) permuting
+    the population permutes the result; (3) no trajectory fails, collided ones score 1e30 and only they; (4) a few
+    trajectories against the oracle, bit for bit (fitness, counts, collision flag)."""
+    c, m = ctx_for(mesh_name)
+    p, po = both_params(stop_on_collision=1)
+    xs = random_population(pop, 2, 4242)
+    whole = c.population_fitness(p, xs, FIXED_POS, 2)
+    fit, col, cnt = whole["fitness"].cpu().numpy(), whole["collision"].cpu().numpy(), _counters(whole)
+    assert fit.shape == (pop,) and np.all(cnt["status"] == 0) and np.all(np.isfinite(fit))
+    assert np.array_equal(fit == 1e30, col != 0) and 0 < col.sum() < pop
+    rng = np.random.default_rng(9)
+    sub = np.sort(rng.choice(pop, 96 if mesh_name == "lp" else 24, replace=False))
+    alone = c.population_fitness(p, xs[sub], FIXED_POS, 2)
+    assert np.array_equal(alone["fitness"].cpu().numpy(), fit[sub])
+    assert np.array_equal(_counters(alone)["n_rhs"], cnt["n_rhs"][sub])
+    if mesh_name == "lp":
+        perm = rng.permutation(pop)
+        assert np.array_equal(c.population_fitness(p, xs[perm], FIXED_POS, 2)["fitness"].cpu().numpy(), fit[perm])
+    order = np.argsort(cnt["n_rhs"][sub])
+    spot = sub[order[len(sub) // 2 - n_spot // 2:len(sub) // 2 - n_spot // 2 + n_spot]]   # median cost: the oracle is a CPU
+    ref = O.population_fitness(m, po, O.default_grid(), xs[spot], FIXED_POS, 2)
+    assert np.array_equal(ref["fitness"], fit[spot]) and np.array_equal(ref["collision"], col[spot])
+    assert np.array_equal(ref["counters"]["n_rhs"], cnt["n_rhs"][spot])
+    assert np.array_equal(ref["n_visited"], whole["n_visited"].cpu().numpy()[spot])

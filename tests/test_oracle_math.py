@@ -48,6 +48,36 @@ def test_minimax_polynomials_of_the_common_path():
     assert ulps(got[nz], ref[nz]).max() <= 2 and np.all(got[~nz] == 0)
 
 
+def test_tier_polynomials_of_the_row_kernels():
+    """far tier (4 coefficients, z^2, t^2 <= 0.0025), middle tier (5, z^2 <= 0.01) and the wide 2 atanh of the remaining
+    rows (11, z^2 <= 0.16): within 2 ulp of libm on the range each tier is used on (the range tests sit just inside)"""
+    rng = np.random.default_rng(8)
+    small = 10.0 ** rng.uniform(-9, -2, 50000)
+    for fn, lim, ref_fn in (("two_atanh_far", 0.05, np.arctanh), ("two_atan_far", 0.05, np.arctan),
+                            ("two_atanh_mid", 0.1, np.arctanh), ("two_atanh_wide", 0.4, np.arctanh)):
+        x = np.concatenate([rng.uniform(-lim, lim, 300000), small, [lim, -lim, 0.0]])
+        got, ref = O.math_probe(fn, x), 2 * ref_fn(x)
+        nz = ref != 0
+        assert ulps(got[nz], ref[nz]).max() <= 2, fn
+        assert np.all(got[~nz] == 0), fn
+    # against 40-digit arithmetic at the upper end of the wide range, where the 11 coefficients matter most
+    import mpmath
+    mpmath.mp.dps = 40
+    z = np.concatenate([rng.uniform(0.3, 0.4, 300), [0.4]])
+    exact = np.array([float(2 * mpmath.atanh(mpmath.mpf(float(v)))) for v in z])
+    assert ulps(O.math_probe("two_atanh_wide", z), exact).max() <= 1
+
+
+def test_high_word_threshold_of_the_wide_rows():
+    """rows outside the far / middle tiers test z^2 < 0x3FC47AE1'00000000 (just below 0.16) in the row kernels"""
+    hi = lambda x: int(np.float64(x).view(np.uint64) >> np.uint64(32))
+    assert hi(0.16) == 0x3FC47AE1 and hi(0.0025) == 0x3F647AE1
+    tw = np.uint64(0x3FC47AE100000000).view(np.float64)
+    tf = np.uint64(0x3F647AE100000000).view(np.float64)
+    assert 0.16 - 4e-8 < tw < 0.16 and 0.0025 - 6e-10 < tf < 0.0025
+    assert tw < 0.1601 and tf < 0.0025      # inside the ranges the polynomials were fitted on
+
+
 def test_sincos():
     rng = np.random.default_rng(2)
     th = np.concatenate([rng.uniform(-100, 100, 400000), rng.uniform(-1e4, 1e4, 100000), [0.0, np.pi / 4, -np.pi / 2]])

@@ -458,7 +458,7 @@ int toss_math_probe(toss_ctx *ctx, int fn, const double *d_a, const double *d_b,
                     double *d_out2, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && (n == 0 || (d_a && d_out)), "toss_math_probe: NULL argument");
-    TOSS_REQUIRE(fn >= 0 && fn <= 10, "toss_math_probe: unknown function id");
+    TOSS_REQUIRE(fn >= 0 && fn <= 14, "toss_math_probe: unknown function id");
     TOSS_REQUIRE(!(fn == 2 || fn == 7) || d_b, "toss_math_probe: this function needs a second operand");
     TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
     return launch_math_probe(ctx, fn, d_a, d_b, n, d_out, d_out2, (cudaStream_t)stream);

@@ -212,6 +212,8 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 // tmath.cuh functions by id, for the bit-parity tests:
 // 0 two_atanh 1 log 2 atan2(a,b) 3 sincos 4 root8 5 root4 6 atan series (8 terms) 7 a/b 8 sqrt
 // 9 2 atanh minimax (z*z <= 0.04) 10 2 atan minimax (t*t <= 0.01)
+// 11 / 12 far-tier 2 atanh / 2 atan (<= 0.0025) 13 middle-tier 2 atanh (<= 0.01) 14 wide 2 atanh (<= 0.16): twice the
+// half values the pair sum works with (the doubling is exact)
 __global__ void math_probe_kernel(int fn, const double *__restrict__ a, const double *__restrict__ b, int64_t n,
                                   double *__restrict__ out, double *__restrict__ out2)
 {
@@ -230,6 +232,10 @@ __global__ void math_probe_kernel(int fn, const double *__restrict__ a, const do
     case 8: r = tm_sqrt(a[i]); break;
     case 9: r = tm_two_atanh_mm(a[i], a[i] * a[i]); break;
     case 10: r = tm_two_atan_mm(a[i], a[i] * a[i]); break;
+    case 11: r = 2.0 * tm_atanh_far(a[i], a[i] * a[i]); break;
+    case 12: r = 2.0 * tm_atan_far(a[i], a[i] * a[i]); break;
+    case 13: r = 2.0 * tm_atanh_mid(a[i], a[i] * a[i]); break;
+    case 14: r = 2.0 * tm_atanh_wide(a[i], a[i] * a[i]); break;
     default: r = __longlong_as_double(0x7ff8000000000000LL);
     }
     out[i] = r;
