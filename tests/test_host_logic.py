@@ -159,6 +159,11 @@ assert champion(full) == (int(np.argmin(truth)), float(truth.min()))
 # a rank with an empty shard (n < world) still takes part in the collective
 one = gather_population_fitness(truth[:1] if dist.get_rank() == 0 else None, 1)
 assert one.shape == (1,) and one[0] == truth[0]
+# a failure seen by ONE rank (a trajectory out of knot capacity) reaches every rank with the same message
+full, flag = gather_population_fitness(truth[lo:hi].copy(), n, local_flag=(dist.get_rank() == 1), return_flag=True)
+assert flag is True and np.array_equal(full, truth)
+full, flag = gather_population_fitness(truth[lo:hi].copy(), n, return_flag=True)
+assert flag is False and np.array_equal(full, truth)
 dist.barrier(); dist.destroy_process_group()
 print("ok", lo, hi)
 '''

@@ -83,10 +83,13 @@ class udp_initial_condition:
         p = params_from_args(args, stop_on_collision=1)
         lo, hi = shard_bounds(len(xs))
         local = ctx.population_fitness_host(p, xs[lo:hi], fixed, n_man, self.knot_capacity) if hi > lo else None
-        if local is not None and (local["counters"]["status"] == 3).any():
-            raise RuntimeError("a trajectory needs more knots than udp.knot_capacity")
-        fit = gather_population_fitness(None if local is None else local["fitness"], len(xs), ctx)
+        short = local is not None and bool((local["counters"]["status"] == 3).any())
+        # the flag travels with the fitness slices: every rank raises, none is left waiting in the collective
+        fit, short = gather_population_fitness(None if local is None else local["fitness"], len(xs), ctx,
+                                               local_flag=short, return_flag=True)
         self.last_batch = local
+        if short:
+            raise RuntimeError("a trajectory needs more knots than udp.knot_capacity")
         return fit
 
     # pygmo deep-copies / pickles the UDP: nothing device-side lives on the object

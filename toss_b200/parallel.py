@@ -33,28 +33,33 @@ def shard_bounds(n: int, rank: int | None = None, world_size: int | None = None)
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_population_fitness(local_fitness, n: int, ctx=None) -> np.ndarray:
-    """All-gather of the per-rank fitness slices into the full length-n vector (identical on every rank)."""
+def gather_population_fitness(local_fitness, n: int, ctx=None, local_flag: bool = False, return_flag: bool = False):
+    """All-gather of the per-rank fitness slices into the full length-n vector (identical on every rank).
+    `local_flag` travels in the same message (one extra element per rank); with `return_flag` the call returns
+    (fitness, any rank's flag) so that a failure seen by one rank is raised by ALL of them after the collective
+    instead of leaving the others waiting in it."""
     d = _dist()
     if d is None:
-        return np.asarray(local_fitness, dtype=np.float64)
+        out = np.asarray(local_fitness, dtype=np.float64)
+        return (out, bool(local_flag)) if return_flag else out
     import torch
     rank, w = d.get_rank(), d.get_world_size()
     nccl = d.get_backend() == "nccl"
     dev = ctx.device if (nccl and ctx is not None) else torch.device("cpu")
     cap = -(-n // w)   # equal-sized send buffers: pad the short shards
-    send = torch.full((cap,), float("nan"), dtype=torch.float64, device=dev)
+    send = torch.full((cap + 1,), float("nan"), dtype=torch.float64, device=dev)
     lo, hi = shard_bounds(n, rank, w)
     if hi > lo:
         send[:hi - lo] = torch.as_tensor(np.asarray(local_fitness, dtype=np.float64)).to(dev)
-    recv = torch.empty(cap * w, dtype=torch.float64, device=dev)
+    send[cap] = 1.0 if local_flag else 0.0
+    recv = torch.empty((cap + 1) * w, dtype=torch.float64, device=dev)
     d.all_gather_into_tensor(recv, send)
-    recv = recv.cpu().numpy().reshape(w, cap)
+    recv = recv.cpu().numpy().reshape(w, cap + 1)
     out = np.empty(n)
     for r in range(w):
         a, b = shard_bounds(n, r, w)
         out[a:b] = recv[r, :b - a]
-    return out
+    return (out, bool((recv[:, cap] != 0.0).any())) if return_flag else out
 
 
 def champion(fitness: np.ndarray):
