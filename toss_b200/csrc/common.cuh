@@ -133,12 +133,20 @@ __device__ __forceinline__ double warp_max(double v)
 
 // equations_of_motion.py:98-117: Quaternion(axis, angle = -(w t)).rotate(x), axis normalised
 // (Euler-Rodrigues form, tests/point_rotation_test.py:47-76).  k = unit axis.
+// the same with sin / cos of the angle -(w t) already in hand (the stepper computes them early, next to the stage point)
+__device__ __forceinline__ void rotate_point_sc(double s, double c, double x, double y, double z, double kx, double ky,
+                                                double kz, double &ox, double &oy, double &oz);
 __device__ __forceinline__ void rotate_point_dev(double t, double x, double y, double z, double kx, double ky,
                                                  double kz, double w, double &ox, double &oy, double &oz)
 {
     double th = -mul_(w, t);
     double s, c;
     tm_sincos(th, s, c);
+    rotate_point_sc(s, c, x, y, z, kx, ky, kz, ox, oy, oz);
+}
+__device__ __forceinline__ void rotate_point_sc(double s, double c, double x, double y, double z, double kx, double ky,
+                                                double kz, double &ox, double &oy, double &oz)
+{
     double cx = sub_(mul_(ky, z), mul_(kz, y));
     double cy = sub_(mul_(kz, x), mul_(kx, z));
     double cz = sub_(mul_(kx, y), mul_(ky, x));

@@ -256,6 +256,12 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 #ifdef K2_PROFILE
     long long prof_wait = 0, prof_comp = 0, prof_wait0 = 0, prof_idle = 0;
     const long long prof_t0 = clock64();
+    // per-section clocks of the owner warp's loop: 0 advance / fetch, 1 stage point, 2 shuffles + rotation,
+    // 3 team publish + ray sweep, 4 gravity sweep, 5 reduction + k store  (sections end at the marks below)
+    long long prof_sec[6] = {0, 0, 0, 0, 0, 0}, prof_last = prof_t0;
+#define K2_MARK(i) { const long long c_ = clock64(); prof_sec[i] += c_ - prof_last; prof_last = c_; }
+#else
+#define K2_MARK(i)
 #endif
     for (;;) {
         // ------------------------------------------------ fetch a trajectory, decode the chromosome
@@ -388,25 +394,38 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         }
 
         // ------------------------------------------------ stage point: ys = y + dt sum_j a_ij k_j
-        double ysc = 0.0, te = t;
+        K2_MARK(0)
+        double ysc = 0.0, te = t, rot_s = 0.0, rot_c = 1.0;
         if (active) {
-            if (lane < 6) {
-                ysc = sy[lane];
-                if (stage > 0) {
-                    double s = 0.0;
-                    for (int j = 0; j < stage; ++j) s = add_(s, mul_(TOSS_RK_A[13 * stage + j], sk[6 * j + lane]));
-                    ysc = add_(ysc, mul_(dt, s));
-                }
-            }
-            if (stage > 0) te = add_(t, mul_(TOSS_RK_C[stage], dt));
+            // One straight-line block: (1) the stage time and sin / cos of the body's rotation angle at it, which depend
+            // on (t, dt, stage) only, and (2) s = sum_{j < stage} a_ij k_j in increasing j (the order is part of the
+            // arithmetic specification).  The two dependency chains are independent, so the scheduler interleaves them;
+            // all twelve coefficient / slope loads are issued up front and the terms beyond `stage` are predicated
+            // off -- one load latency per stage point instead of one per remainder block of a loop with a run-time
+            // trip count.  Lanes 6..31 mirror lane 5 instead of branching around the block (their value is not used).
+            // This chain is on the critical path of a small population, where the latency of an RHS evaluation counts.
+            const int l6 = lane < 6 ? lane : 5;
+            te = stage > 0 ? add_(t, mul_(TOSS_RK_C[stage], dt)) : t;
+            tm_sincos(-mul_(p.spin_velocity, te), rot_s, rot_c);
+            double pr_[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) pr_[j] = mul_(TOSS_RK_A[13 * stage + j], sk[6 * j + l6]);
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < 12; ++j)
+                if (j < stage) s = add_(s, pr_[j]);
+            const double y0 = sy[l6];
+            ysc = stage > 0 ? add_(y0, mul_(dt, s)) : y0;
         }
+        K2_MARK(1)
         const double qx = __shfl_sync(0xffffffffu, ysc, 0), qy = __shfl_sync(0xffffffffu, ysc, 1),
                      qz = __shfl_sync(0xffffffffu, ysc, 2);
         const double vsh = __shfl_sync(0xffffffffu, ysc, (lane + 3) & 31);   // lanes 0..2 receive ys[3..5]
         double Px = qx, Py = qy, Pz = qz;
         if (active && p.activate_rotation)
-            rotate_point_dev(te, qx, qy, qz, a.axis.x, a.axis.y, a.axis.z, p.spin_velocity, Px, Py, Pz);
+            rotate_point_sc(rot_s, rot_c, qx, qy, qz, a.axis.x, a.axis.y, a.axis.z, Px, Py, Pz);
 
+        K2_MARK(2)
         if (team_alive) {   // tell the helpers what this sweep is
             if (lane == 0) {
                 tP[0] = Px;
@@ -434,6 +453,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         }
 
         // ------------------------------------------------ gravity sweep over all face pairs
+        K2_MARK(3)
         double ax = 0.0, ay = 0.0, az = 0.0, pv = 0.0;
         if (kProxy) {
             for (int m = lane; m < a.proxy_n; m += 32) {
@@ -533,6 +553,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 }
             }
         }
+        K2_MARK(4)
         if (!active) continue;
         bool post_event = false;   // run the tail of the stage-0 logic (after the event test, if there was one)
         if (ray_sweep) {
@@ -546,11 +567,10 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         az = warp_sum(az);
         ++n_rhs;
         // k_stage = [ys[3..5], -g_pkg]   (equations_of_motion.py:59,92-95)
-        double kc = 0.0;
-        if (lane < 3) kc = vsh;
-        else if (lane == 3) kc = kProxy ? ax : -((a.Grho + a.Grho) * ax);   // the pair sum runs in exact halves
-        else if (lane == 4) kc = kProxy ? ay : -((a.Grho + a.Grho) * ay);
-        else if (lane == 5) kc = kProxy ? az : -((a.Grho + a.Grho) * az);
+        // (selects, not branches: lanes 3, 4 and 5 would otherwise serialise three copies of the same two instructions)
+        const double asel = lane == 3 ? ax : (lane == 4 ? ay : az);
+        const double gsel = kProxy ? asel : -((a.Grho + a.Grho) * asel);   // the pair sum runs in exact halves
+        const double kc = lane < 3 ? vsh : gsel;
         if (lane < 6) sk[6 * stage + lane] = kc;
         __syncwarp();
         if (stage == 0) {
@@ -578,6 +598,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         }
 
         // ------------------------------------------------ advance the state machine
+        K2_MARK(5)
         if (post_event) {
             if (after_accept) {
                 after_accept = 0;
@@ -695,6 +716,8 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         atomicAdd(pr + 5, (unsigned long long)prof_idle);
         atomicAdd(pr + 8 + (wid & 7), (unsigned long long)prof_wait);
         atomicAdd(pr + 16 + (wid & 7), (unsigned long long)prof_comp);
+        if (kTeam == 1 || rank == 0)
+            for (int i = 0; i < 6; ++i) atomicAdd(pr + 24 + i, (unsigned long long)prof_sec[i]);
     }
 #endif
     // drain the TMA copies still in flight before the CTA's shared memory goes away
