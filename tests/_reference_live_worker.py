@@ -1,0 +1,102 @@
+"""Run by tests/test_host_vs_reference_live.py in a SUBPROCESS, in the build container only (needs /root/reference):
+imports the reference's own modules from where they lie, with inert stand-ins for the third-party packages that are
+not installed here (the same ones tools/gen_golden_fixtures.py uses; none of them does arithmetic on this path), runs
+the reference's HOST-side functions on seeded inputs and writes inputs and outputs to an .npz.  Test infrastructure."""
+import sys
+import types
+
+import numpy as np
+
+ref_root, out_path = sys.argv[1], sys.argv[2]
+sys.path.insert(0, ref_root)
+
+
+class _Inert(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        m = _Inert(self.__name__ + "." + name)
+        setattr(self, name, m)
+        return m
+
+    def __call__(self, *a, **k):
+        return self
+
+    def __iter__(self):          # `_, _ = tgen.tetrahedralize()` (mesh_utility.py:65: the result feeds plotting only)
+        return iter((self, self))
+
+
+for name in ["tetgen", "tetgen.pytetgen", "polyhedral_gravity", "polyhedral_gravity.model", "desolver",
+             "desolver.backend", "pykep", "matplotlib", "matplotlib.pyplot", "matplotlib.patches", "mpl_toolkits",
+             "mpl_toolkits.mplot3d", "pyvista", "pyquaternion", "pygmo"]:
+    sys.modules[name] = _Inert(name)
+
+
+class DotMap(dict):
+    def __init__(self, *a, _dynamic=True, **k):
+        super().__init__(*a, **k)
+        for key, v in list(self.items()):
+            if isinstance(v, dict) and not isinstance(v, DotMap):
+                self[key] = DotMap(v)
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+dm = types.ModuleType("dotmap")
+dm.DotMap = DotMap
+sys.modules["dotmap"] = dm
+try:
+    import toml  # noqa: F401
+except ImportError:
+    import tomllib
+    tm = types.ModuleType("toml")
+    tm.load = lambda f: tomllib.loads(f.read()) if hasattr(f, "read") else tomllib.load(open(f, "rb"))
+    sys.modules["toml"] = tm
+
+import os  # noqa: E402
+os.chdir(ref_root)                       # the cfg's mesh_path is relative to the repository root
+from toss.optimization.setup_parameters import setup_parameters  # noqa: E402
+from toss.optimization.setup_state import setup_initial_state_domain  # noqa: E402
+from toss.trajectory.equations_of_motion import setup_spin_axis  # noqa: E402
+from toss.fitness.fitness_function_utils import (create_spherical_tensor_grid, cart2sphere, sphere2cart,  # noqa: E402
+                                                 _compute_squared_distance)
+
+out = {}
+args = setup_parameters()
+for sec in ("problem", "body", "integrator", "optimization", "algorithm", "chromosome", "mesh"):
+    for k, v in args[sec].items():
+        if k in ("body", "evaluable"):
+            continue
+        if v is None:
+            out[f"args.{sec}.{k}"] = np.array("None")
+        elif isinstance(v, (bool, int, float, str, np.ndarray, list)):
+            out[f"args.{sec}.{k}"] = np.asarray(v)
+rng = np.random.default_rng(31)
+xyz = rng.normal(size=(3, 500)) * 8000.0
+out["xyz"] = xyz
+out["cart2sphere"] = np.vstack(cart2sphere(xyz[0], xyz[1], xyz[2]))
+r, th, ph = rng.uniform(1, 2e4, 500), rng.uniform(-np.pi / 2, np.pi / 2, 500), rng.uniform(-np.pi, np.pi, 500)
+out["rtp"] = np.vstack([r, th, ph])
+out["sphere2cart"] = np.vstack(sphere2cart(r, th, ph))
+out["sqdist"] = _compute_squared_distance(xyz, 4000.0)
+for i, (dt, rmin, rmax, scale) in enumerate([(100, 4000, 12500, 40), (100, 4000, 12500, 8), (50, 3000, 9000, 15.5)]):
+    v = rng.normal(size=3)
+    g = create_spherical_tensor_grid(dt, rmin, rmax, scale, v)
+    out[f"grid{i}_v"] = v
+    for nme, arr in zip("r theta phi bool".split(), g):
+        out[f"grid{i}_{nme}"] = np.asarray(arr)
+for n_fixed in (0, 3, 7):
+    for n_man in (0, 1, 3):
+        lb, ub = setup_initial_state_domain(np.zeros(n_fixed), 0, 604800, n_man, 4, args.chromosome)
+        out[f"bounds_{n_fixed}_{n_man}_lo"], out[f"bounds_{n_fixed}_{n_man}_hi"] = np.asarray(lb, float), np.asarray(ub, float)
+a2 = DotMap({"body": {"declination": 64.0, "right_ascension": 69.0}})
+out["spin_axis_64_69"] = np.asarray(setup_spin_axis(a2))
+np.savez(out_path, **out)
+print("ok", len(out))

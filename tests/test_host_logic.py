@@ -179,3 +179,15 @@ def test_gather_over_two_gloo_ranks(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert outs[0].strip().endswith("ok 0 6") and outs[1].strip().endswith("ok 6 11")
+
+
+def test_grid_builder_input_assertions_are_the_reference_s():
+    """fitness_function_utils.py:251-254 asserts on its four inputs (not on the resulting step counts): a spacing larger
+    than the shell gives an EMPTY axis, which toss_grid_upload then refuses."""
+    import toss_b200 as T
+    v = np.array([0.1, 0.2, -0.3])
+    for bad in ((0, 4000, 12500, 40), (100, 0, 12500, 40), (100, 4000, 4000, 40), (100, 4000, 12500, 0)):
+        with pytest.raises(AssertionError):
+            T.create_spherical_tensor_grid(*bad, v)
+    r, th, ph, bt = T.create_spherical_tensor_grid(100, 4000, 12500, 400, v)     # 15 km per step > 8.5 km of shell
+    assert len(r) == 0 and bt.shape == (0, len(th), len(ph)) and bt.dtype == bool

@@ -57,15 +57,18 @@ def update_spherical_tensor_grid(number_of_spacecrafts: int, spin_axis: np.ndarr
 def create_spherical_tensor_grid(time_step: int, radius_min: float, radius_max: float,
                                  max_velocity_scaling_factor: float,
                                  fixed_velocity: np.ndarray) -> Union[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
-    """Grid spacing from the distance travelled in one time step at the scaled sample velocity (:231-279)."""
+    """Grid spacing from the distance travelled in one time step at the scaled sample velocity (:231-279); the
+    reference's own input assertions (:251-254)."""
+    assert (time_step > 0)
+    assert (radius_min > 0)
+    assert (radius_max > radius_min)
+    assert (max_velocity_scaling_factor > 0)
     max_velocity = np.max(np.linalg.norm(fixed_velocity)) * max_velocity_scaling_factor
     max_distance_traveled = max_velocity * time_step
     r_steps = np.floor((radius_max - radius_min) / max_distance_traveled)
     theta_steps = np.floor(np.pi * radius_min / max_distance_traveled)
     phi_steps = np.floor(2 * np.pi * radius_min / max_distance_traveled)
-    assert r_steps > 0
-    assert theta_steps > 0
-    assert phi_steps > 0
+    # (a spacing larger than the shell gives an empty axis, as in the reference; uploading such a grid is refused)
     r = np.linspace(radius_min, radius_max, int(r_steps))
     theta = np.linspace(-np.pi / 2, np.pi / 2, int(theta_steps))
     phi = np.linspace(-np.pi, np.pi, int(phi_steps))
