@@ -96,6 +96,57 @@ for n_fixed in (0, 3, 7):
     for n_man in (0, 1, 3):
         lb, ub = setup_initial_state_domain(np.zeros(n_fixed), 0, 604800, n_man, 4, args.chromosome)
         out[f"bounds_{n_fixed}_{n_man}_lo"], out[f"bounds_{n_fixed}_{n_man}_hi"] = np.asarray(lb, float), np.asarray(ub, float)
+# ---- the reference's own compute_trajectory (decode, int32 truncation, sort, merge of simultaneous manoeuvres, the
+# segment loop that REPLACES the velocity) around a stand-in integrator that returns its initial state: what is
+# recorded is every (t0, tf, initial state) the reference hands to desolver, plus the intervals it returns
+import toss.trajectory.compute_trajectory as ct  # noqa: E402
+
+
+class _Traj:
+    def __init__(self, x):
+        self.y = np.array([x], dtype=np.float64)
+        self.events = []
+
+
+_calls = []
+
+
+def _fake_integrate(func, x, a):
+    _calls.append(np.concatenate(([float(a.integrator.t0), float(a.integrator.tf)], np.asarray(x, dtype=np.float64))))
+    return _Traj(np.array(x, dtype=np.float64))
+
+
+ct.integrate_system = _fake_integrate
+ct.point_is_outside_mesh = lambda pts, v, f: np.ones(len(pts), dtype=bool)
+T_END = 20000.0
+args.problem.start_time, args.problem.final_time = 0.0, T_END
+cases = []
+for n_man in (0, 1, 2, 3, 5):
+    for rep in range(6):
+        x = np.concatenate((rng.normal(size=3) * 6000.0, [rng.uniform(0, 1)], rng.uniform(-1, 1, 3)))
+        tm = rng.uniform(1, T_END - 1, n_man)
+        if n_man >= 2 and rep % 3 == 1:
+            tm[1] = np.floor(tm[0]) + 0.75          # equal after the int32 truncation
+            tm[0] = np.floor(tm[0]) + 0.25
+        if n_man >= 3 and rep % 3 == 2:
+            tm[:] = np.floor(tm[0]) + rng.uniform(0, 0.99, n_man)   # all simultaneous
+        if n_man >= 3 and rep == 3:
+            tm[2] = np.floor(tm[0]) + 0.5           # first and third equal, second in between or not
+        for k in range(n_man):
+            x = np.concatenate((x, [tm[k], rng.uniform(0, 2.5)], rng.uniform(-1, 1, 3)))
+        cases.append((n_man, x))
+for i, (n_man, x) in enumerate(cases):
+    args.problem.number_of_maneuvers = n_man
+    _calls.clear()
+    collided, objs, iv = ct.compute_trajectory(x.copy(), args, None)
+    out[f"traj{i}_x"] = x
+    out[f"traj{i}_nman"] = np.array(n_man)
+    out[f"traj{i}_intervals"] = np.asarray(iv, dtype=np.float64)
+    out[f"traj{i}_calls"] = np.array(_calls)
+    assert collided is False and len(objs) == len(_calls)
+out["traj_n"] = np.array(len(cases))
+out["traj_T_END"] = np.array(T_END)
+
 a2 = DotMap({"body": {"declination": 64.0, "right_ascension": 69.0}})
 out["spin_axis_64_69"] = np.asarray(setup_spin_axis(a2))
 np.savez(out_path, **out)

@@ -74,3 +74,29 @@ def test_chromosome_bounds_and_spin_axis_equal_the_reference(ref):
             assert np.array_equal(np.asarray(ub, float), ref[f"bounds_{n_fixed}_{n_man}_hi"])
     a2 = DotMap({"body": DotMap({"declination": 64.0, "right_ascension": 69.0})})
     assert np.array_equal(np.asarray(T.setup_spin_axis(a2)), ref["spin_axis_64_69"])
+
+
+def test_manoeuvre_decode_and_segment_loop_equal_the_reference(ref):
+    """The reference's OWN compute_trajectory (compute_trajectory.py:53-136: v0 = v_mag * v_dir, int32 truncation of the
+    manoeuvre times, stable sort, merge of simultaneous manoeuvres, velocity REPLACED at a manoeuvre) run around a
+    stand-in integrator, against the oracle's trajectory on the same chromosomes: same integration intervals, same
+    number of segments, the same velocity at the first knot of every segment, the same initial state."""
+    from oracle import oracle as O
+    v, f = O.load_mesh("lllp")
+    m = O.Mesh(v, f)
+    t_end = float(ref["traj_T_END"])
+    n_merged = 0
+    for i in range(int(ref["traj_n"])):
+        x, n_man = ref[f"traj{i}_x"], int(ref[f"traj{i}_nman"])
+        iv, calls = ref[f"traj{i}_intervals"], ref[f"traj{i}_calls"]
+        p = O.default_params(final_time=t_end, activate_event=0, rtol=1e-6, atol=1e-6)
+        tr = O.compute_trajectory(m, p, x, n_man)
+        assert np.array_equal(tr.intervals, iv), (i, tr.intervals, iv)
+        assert tr.n_seg == len(calls) == len(iv) - 1
+        n_merged += int(len(iv) - 1 < n_man + 1)
+        for k in range(tr.n_seg):
+            t_k, y_k, _ = tr.segment(k)
+            assert t_k[0] == calls[k, 0] and t_k[-1] == calls[k, 1]
+            assert np.array_equal(y_k[0, 3:6], calls[k, 5:8]), (i, k)      # v0, then the (merged) dv of the manoeuvre
+        assert np.array_equal(tr.y[0, 0:3], calls[0, 2:5])
+    assert n_merged >= 4          # the simultaneous-manoeuvre cases did merge
