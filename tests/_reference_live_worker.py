@@ -147,6 +147,78 @@ for i, (n_man, x) in enumerate(cases):
 out["traj_n"] = np.array(len(cases))
 out["traj_T_END"] = np.array(T_END)
 
+# ---- coverage / voxel update / all nine fitness functions on random walks and on constructed TIES --------------------
+class Quaternion:
+    """axis-angle unit quaternion; rotate(v) = q v q* (pyquaternion semantics, axis normalised) -- the one stand-in
+    that does arithmetic (the same one tools/gen_golden_fixtures.py uses)"""
+
+    def __init__(self, axis, angle):
+        axis = np.asarray(axis, dtype=np.float64)
+        axis = axis / np.linalg.norm(axis)
+        self.w = np.cos(angle / 2.0)
+        self.v = axis * np.sin(angle / 2.0)
+
+    def rotate(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        t = 2.0 * np.cross(self.v, x)
+        return x + self.w * t + np.cross(self.v, t)
+
+
+import toss.fitness.fitness_function_utils as ffu  # noqa: E402
+import toss.trajectory.equations_of_motion as eom  # noqa: E402
+for mod in (ffu, eom):
+    if hasattr(mod, "Quaternion"):
+        mod.Quaternion = Quaternion
+from toss.fitness.fitness_functions import get_fitness  # noqa: E402
+from toss.fitness.fitness_function_enums import FitnessFunctions  # noqa: E402
+
+axis = np.array([0.15709817, 0.40925472, 0.89879405])
+wspin = 2 * np.pi / 43416.0
+gr, gth, gph, _ = create_spherical_tensor_grid(100, 4000, 12500, 40, np.array([-0.02826052, 0.1784372, -0.29885126]))
+out["cov_grid_r"], out["cov_grid_theta"], out["cov_grid_phi"] = gr, gth, gph
+cov_cases = []
+for ci in range(24):
+    N = int(rng.choice([1, 2, 3, 5, 29, 120, 400]))
+    nsc = int(rng.choice([1, 2, 3, 4, 7]))
+    step = rng.normal(size=(3, N)) * rng.choice([30.0, 300.0, 1500.0])
+    pos = (rng.normal(size=(3, 1)) * rng.choice([2500.0, 5000.0, 9000.0])) + np.cumsum(step, axis=1)
+    ts = np.arange(N) * 100.0
+    w_case = wspin
+    if ci % 6 == 4:        # ties: no rotation (angle exactly 0), samples exactly midway between two r grid points,
+        w_case = 0.0       # on the equator (theta = 0 is midway between the two middle points of an even theta grid)
+        mids = 0.5 * (gr[:-1] + gr[1:])
+        k = rng.integers(0, len(mids), N)
+        sgn = rng.choice([-1.0, 1.0], N)
+        pos = np.vstack((sgn * mids[k], np.zeros(N), np.zeros(N)))
+    if ci % 6 == 5:        # nothing inside the shell
+        pos = pos / np.linalg.norm(pos, axis=0) * rng.uniform(13000.0, 30000.0, N)
+    bt = rng.random((len(gr), len(gth), len(gph))) < rng.choice([0.0, 0.15, 0.9])
+    cov_cases.append((N, nsc, w_case, pos, ts, bt))
+for ci, (N, nsc, w_case, pos, ts, bt) in enumerate(cov_cases):
+    vel = np.zeros_like(pos)
+    cov = ffu.compute_space_coverage(nsc, axis, w_case, pos, vel, ts, 4000.0, 12500.0, gr, gth, gph, bt.copy())
+    new_bt = ffu.update_spherical_tensor_grid(nsc, axis, w_case, pos, vel, ts, 4000.0, 12500.0, gr, gth, gph, bt.copy())
+    fa = DotMap({"body": DotMap({"spin_axis": axis, "spin_velocity": w_case}),
+                 "problem": DotMap({"number_of_spacecrafts": nsc, "target_squared_altitude": 8000.0 ** 2,
+                                    "radius_inner_bounding_sphere": 4000.0, "radius_outer_bounding_sphere": 12500.0,
+                                    "penalty_scaling_factor": 0.1,
+                                    "maximal_measurement_sphere_volume": (4 / 3) * np.pi * 35.95398913 ** 3,
+                                    "total_measurable_volume": (4 / 3) * np.pi * (12500.0 ** 3 - 4000.0 ** 3),
+                                    "tensor_grid_r": gr, "tensor_grid_theta": gth, "tensor_grid_phi": gph,
+                                    "bool_tensor": bt.copy()})})
+    fits = []
+    for e in range(1, 10):
+        try:
+            fits.append(float(get_fitness(FitnessFunctions(e), fa, pos, vel, ts)))
+        except Exception:      # e.g. the covered-volume functions on a single sample
+            fits.append(np.nan)
+    out[f"cv{ci}_pos"], out[f"cv{ci}_ts"], out[f"cv{ci}_bt"] = pos, ts, bt
+    out[f"cv{ci}_meta"] = np.array([N, nsc, w_case])
+    out[f"cv{ci}_coverage"] = np.float64(cov)
+    out[f"cv{ci}_new_bt"] = np.asarray(new_bt, dtype=bool)
+    out[f"cv{ci}_fitness"] = np.array(fits)
+out["cv_n"] = np.array(len(cov_cases))
+
 a2 = DotMap({"body": {"declination": 64.0, "right_ascension": 69.0}})
 out["spin_axis_64_69"] = np.asarray(setup_spin_axis(a2))
 np.savez(out_path, **out)

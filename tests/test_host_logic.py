@@ -191,3 +191,16 @@ def test_grid_builder_input_assertions_are_the_reference_s():
             T.create_spherical_tensor_grid(*bad, v)
     r, th, ph, bt = T.create_spherical_tensor_grid(100, 4000, 12500, 400, v)     # 15 km per step > 8.5 km of shell
     assert len(r) == 0 and bt.shape == (0, len(th), len(ph)) and bt.dtype == bool
+
+
+def test_covered_volume_of_a_single_sample_fails_like_the_reference():
+    """estimate_covered_volume copies the second radius into the first (fitness_function_utils.py:30-31): with one
+    sample the reference raises IndexError; so do the mirrors, before anything reaches the device."""
+    import toss_b200 as T
+    one = np.array([[5000.0], [100.0], [200.0]])
+    with pytest.raises(IndexError):
+        T.estimate_covered_volume(one)
+    with pytest.raises(IndexError):
+        T.covered_volume(1.0e5, one)
+    with pytest.raises(IndexError):
+        T.total_covered_volume(1.0e12, one)

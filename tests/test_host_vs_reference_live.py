@@ -100,3 +100,35 @@ def test_manoeuvre_decode_and_segment_loop_equal_the_reference(ref):
             assert np.array_equal(y_k[0, 3:6], calls[k, 5:8]), (i, k)      # v0, then the (merged) dv of the manoeuvre
         assert np.array_equal(tr.y[0, 0:3], calls[0, 2:5])
     assert n_merged >= 4          # the simultaneous-manoeuvre cases did merge
+
+
+def test_coverage_voxels_and_fitness_fuzz_equal_the_reference(ref):
+    """24 random walks (1 .. 400 samples, 1 .. 7 spacecraft chunks, empty / sparse / dense previous tensors, samples
+    inside, outside and across the shell) plus constructed TIES (no rotation, samples exactly midway between two r
+    grid points and on the equator, where theta = 0 is midway between the two middle points of the even theta grid:
+    argmin takes the first minimum) through the reference's compute_space_coverage / update_spherical_tensor_grid /
+    get_fitness(1..9), against the oracle: voxel tensors exact, values to 1e-12."""
+    from oracle import oracle as O
+    g = (ref["cov_grid_r"], ref["cov_grid_theta"], ref["cov_grid_phi"])
+    axis = np.array([0.15709817, 0.40925472, 0.89879405])
+    n_ties = 0
+    for ci in range(int(ref["cv_n"])):
+        N, nsc, w = ref[f"cv{ci}_meta"]
+        N, nsc = int(N), int(nsc)
+        pos, ts, bt = ref[f"cv{ci}_pos"], ref[f"cv{ci}_ts"], ref[f"cv{ci}_bt"]
+        want_bt, want_cov, want_fit = ref[f"cv{ci}_new_bt"], float(ref[f"cv{ci}_coverage"]), ref[f"cv{ci}_fitness"]
+        n_ties += int(w == 0.0)
+        cov, nvis, newt = O.space_coverage(nsc, axis, float(w), pos, ts, 4000.0, 12500.0, (*g, bt),
+                                           return_visited=True, return_tensor=True)
+        assert np.array_equal(newt, want_bt), ci
+        assert nvis == int(want_bt.sum()), ci
+        assert abs(cov - want_cov) <= 1e-12 * max(abs(want_cov), 1e-300), (ci, cov, want_cov)
+        assert np.array_equal(O.update_tensor(nsc, axis, float(w), pos, ts, 4000.0, 12500.0, (*g, bt)), want_bt), ci
+        p = O.default_params(number_of_spacecrafts=nsc, spin_axis=axis, spin_velocity=float(w),
+                             target_squared_altitude=8000.0 ** 2)
+        for e in range(1, 10):
+            if np.isnan(want_fit[e - 1]):
+                continue
+            got = O.get_fitness(e, p, pos, ts, (*g, bt))
+            assert abs(got - want_fit[e - 1]) <= 1e-12 * max(abs(want_fit[e - 1]), 1e-300), (ci, e, got, want_fit[e - 1])
+    assert n_ties >= 3

@@ -95,8 +95,10 @@ def sphere2cart(r, theta, phi) -> tuple:
 def estimate_covered_volume(positions: np.ndarray) -> float:
     """Sum of the measurement-sphere volumes along the trajectory (:8-38); the GPU evaluates the same sum
     inside fitness ids 4-7 -- this helper returns it alone."""
-    ctx = any_context()
     pos = _positions_3xN(positions)
+    if pos.shape[1] < 2:      # the reference fails on `sphere_radii[0] = sphere_radii[1]` (:30-31)
+        raise IndexError("index 1 is out of bounds for axis 0 with size 1")
+    ctx = any_context()
     p = default_params(total_measurable_volume=1.0)
     if ctx.grid_shape is None:
         ctx.upload_grid([1.0], [0.0], [0.0], np.zeros((1, 1, 1), dtype=np.uint8))

@@ -8,8 +8,12 @@ from .fitness_function_utils import _positions_3xN, compute_space_coverage
 
 
 def _eval(fn: int, p, positions, timesteps=None) -> float:
-    ctx = any_context()
     pos = _positions_3xN(positions)
+    if fn in (4, 5, 6, 7) and pos.shape[1] < 2:
+        # estimate_covered_volume needs two samples: the reference fails on `sphere_radii[0] = sphere_radii[1]`
+        # (fitness_function_utils.py:30-31) -- same exception type here
+        raise IndexError("index 1 is out of bounds for axis 0 with size 1")
+    ctx = any_context()
     if ctx.grid_shape is None:   # ids 1..7 never touch the grid, but the kernel signature carries one
         ctx.upload_grid([1.0], [0.0], [0.0], np.zeros((1, 1, 1), dtype=np.uint8))
     ts = np.zeros(pos.shape[1]) if timesteps is None else np.ascontiguousarray(timesteps, dtype=np.float64)
