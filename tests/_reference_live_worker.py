@@ -219,6 +219,16 @@ for ci, (N, nsc, w_case, pos, ts, bt) in enumerate(cov_cases):
     out[f"cv{ci}_fitness"] = np.array(fits)
 out["cv_n"] = np.array(len(cov_cases))
 
+# ---- is_outside on many points hugging the surface (where the +z ray parity is decided by few faces) -----------------
+from toss.mesh.mesh_utility import is_outside, create_mesh  # noqa: E402
+for mesh_name, n in (("lllp", 3000), ("llp", 3000), ("lp", 600)):
+    _, mv, mf, _ = create_mesh(f"3dmeshes/churyumov-gerasimenko_{mesh_name}.pk")
+    cen = mv[mf].mean(axis=1)                                   # face centroids
+    pick = rng.integers(0, len(cen), n)
+    pts = cen[pick] * rng.uniform(0.6, 1.4, (n, 1)) + rng.normal(size=(n, 3)) * 30.0
+    out[f"io_{mesh_name}_pts"] = pts
+    out[f"io_{mesh_name}_flags"] = np.asarray(is_outside(pts, mv, mf), dtype=bool)
+
 a2 = DotMap({"body": {"declination": 64.0, "right_ascension": 69.0}})
 out["spin_axis_64_69"] = np.asarray(setup_spin_axis(a2))
 np.savez(out_path, **out)

@@ -132,3 +132,15 @@ def test_coverage_voxels_and_fitness_fuzz_equal_the_reference(ref):
             got = O.get_fitness(e, p, pos, ts, (*g, bt))
             assert abs(got - want_fit[e - 1]) <= 1e-12 * max(abs(want_fit[e - 1]), 1e-300), (ci, e, got, want_fit[e - 1])
     assert n_ties >= 3
+
+
+@pytest.mark.parametrize("mesh_name", ["lllp", "llp", "lp"])
+def test_is_outside_fuzz_equals_the_reference(ref, mesh_name):
+    """mesh_utility.is_outside (Moeller-Trumbore, +z ray, hit parity) on thousands of points within +-40 % of the
+    surface, against the oracle's ray casting: every flag equal, and both classes well represented."""
+    from oracle import oracle as O
+    v, f = O.load_mesh(mesh_name)
+    pts, want = ref[f"io_{mesh_name}_pts"], ref[f"io_{mesh_name}_flags"]
+    got = O.is_outside(O.Mesh(v, f), pts)
+    assert np.array_equal(np.asarray(got, dtype=bool), want)
+    assert 0.2 < want.mean() < 0.8
