@@ -229,6 +229,43 @@ for mesh_name, n in (("lllp", 3000), ("llp", 3000), ("lp", 600)):
     out[f"io_{mesh_name}_pts"] = pts
     out[f"io_{mesh_name}_flags"] = np.asarray(is_outside(pts, mv, mf), dtype=bool)
 
+# ---- the reference's resampling code fed with segment objects built from REAL trajectories (the oracle's knots and its
+# dense output behind the name-mangled callable trajectory_tools.py:67 uses): pins the sample -> segment plumbing end to end
+from pathlib import Path as _P  # noqa: E402
+sys.path.insert(0, str(_P(__file__).resolve().parent.parent))
+from oracle import oracle as _O  # noqa: E402
+from toss.trajectory.trajectory_tools import get_trajectory_fixed_step, get_trajectory_adaptive_step  # noqa: E402
+
+
+class _Seg:
+    def __init__(self, t, y, f):
+        self.t, self.y, self._f = t, y, f
+
+    def _OdeSystem__sol(self, tq):
+        return _O.dense_eval(self.t, self.y, self._f, np.atleast_1d(np.asarray(tq, dtype=np.float64)))
+
+
+_mv, _mf = _O.load_mesh("lllp")
+_mesh = _O.Mesh(_mv, _mf)
+rs_cases = [(0, 86400.0, 100.0), (1, 86400.0, 100.0), (2, 50000.0, 250.0), (3, 20000.0, 7.0), (3, 20000.0, 100.0)]
+for i, (n_man, t_end, period) in enumerate(rs_cases):
+    x = np.concatenate(([-135.13402075, -4089.53592604, 6050.17636635], [rng.uniform(0.2, 0.6)], rng.uniform(-1, 1, 3)))
+    tm = rng.uniform(1, t_end - 1, n_man)
+    if n_man == 3 and period == 100.0:
+        tm = np.array([5000.0, 5000.4, 7300.0])          # a merged pair, and manoeuvres exactly ON sample times
+    for k in range(n_man):
+        x = np.concatenate((x, [tm[k], rng.uniform(0, 0.3)], rng.uniform(-1, 1, 3)))
+    p_ = _O.default_params(final_time=t_end, measurement_period=period, activate_event=0, rtol=1e-8, atol=1e-8)
+    tr = _O.compute_trajectory(_mesh, p_, x, n_man)
+    objs = [_Seg(*tr.segment(k)) for k in range(tr.n_seg)]
+    ra = DotMap({"problem": DotMap({"start_time": 0.0, "final_time": t_end, "measurement_period": period})})
+    pos, vel, ts = get_trajectory_fixed_step(ra, objs)
+    st, tt = get_trajectory_adaptive_step(objs)
+    out[f"rs{i}_x"], out[f"rs{i}_meta"] = x, np.array([n_man, t_end, period])
+    out[f"rs{i}_pos"], out[f"rs{i}_vel"], out[f"rs{i}_ts"] = pos, vel, ts
+    out[f"rs{i}_states"], out[f"rs{i}_times"] = st, tt
+out["rs_n"] = np.array(len(rs_cases))
+
 a2 = DotMap({"body": {"declination": 64.0, "right_ascension": 69.0}})
 out["spin_axis_64_69"] = np.asarray(setup_spin_axis(a2))
 np.savez(out_path, **out)

@@ -144,3 +144,21 @@ def test_is_outside_fuzz_equals_the_reference(ref, mesh_name):
     got = O.is_outside(O.Mesh(v, f), pts)
     assert np.array_equal(np.asarray(got, dtype=bool), want)
     assert 0.2 < want.mean() < 0.8
+
+
+def test_resampling_plumbing_on_real_trajectories_equals_the_reference(ref):
+    """The reference's get_trajectory_fixed_step / get_trajectory_adaptive_step run on segment objects built from the
+    oracle's knots and dense output (a merged manoeuvre pair, manoeuvres exactly on sample times, a 7 s period), against
+    the oracle's own resampler on the same trajectory: identical samples, times and concatenated knots."""
+    from oracle import oracle as O
+    v, f = O.load_mesh("lllp")
+    m = O.Mesh(v, f)
+    for i in range(int(ref["rs_n"])):
+        n_man, t_end, period = ref[f"rs{i}_meta"]
+        p = O.default_params(final_time=float(t_end), measurement_period=float(period), activate_event=0,
+                             rtol=1e-8, atol=1e-8)
+        tr = O.compute_trajectory(m, p, ref[f"rs{i}_x"], int(n_man))
+        pos, vel, ts = O.fixed_step(p, tr)
+        assert np.array_equal(ts, ref[f"rs{i}_ts"]), i
+        assert np.array_equal(pos, ref[f"rs{i}_pos"]) and np.array_equal(vel, ref[f"rs{i}_vel"]), i
+        assert np.array_equal(tr.y.T, ref[f"rs{i}_states"]) and np.array_equal(tr.t, ref[f"rs{i}_times"]), i
