@@ -183,6 +183,34 @@ int toss_population_fitness_host(toss_ctx *ctx, const toss_params *p, const doub
                                  double *h_fitness, int32_t *h_collision, toss_counters *h_counters,
                                  int64_t *h_n_visited);
 
+/* ---- one population over several GPUs --------------------------------------------------------
+ * Replaces the process pool of pg.mp_bfe (toss.py:110; every worker evaluates a share of the generation,
+ * scripts/scaling_performance_benchmark.py:126-137).  One process per GPU; every rank holds the whole pop x dim
+ * chromosome matrix (a pygmo batch_fitness call hands it to all of them) and evaluates the rows DEALT to it:
+ *   toss_predict_cost   cost key of each row of d_x (a short proxy integration through a mascon model of the body;
+ *                       all zero when the mesh is so small that the proxy would not pay) -> d_cost int32[pop].
+ *                       Each rank predicts a contiguous slice; the host all-gathers the slices (NCCL).
+ *   toss_cost_order     d_order int32[n] = the rows in longest-first order, ties by index: a pure function of d_cost,
+ *                       identical on every rank.
+ *   toss_deal_rows      rank g's shard: d_x_local[j] = d_x[d_order[g + j*world]], j < ceil((n - g) / world) -- equal
+ *                       predicted work for every rank, each shard already longest-first.
+ *   toss_set_queue_order(ctx, 1) tells toss_population_fitness / toss_propagate that the rows come pre-ordered (no
+ *                       second proxy run); 0 restores the default (the launcher orders its queue itself).
+ *   toss_pack_result    d_send double[cap + 2] = the shard's fitness padded with NaN to cap | #trajectories with
+ *                       status 3 | #with status 1 or 2 -- the all-gather payload.
+ *   toss_unpack_result  d_recv double[world][cap + 2] (the gathered payloads) -> d_fitness double[n] in population
+ *                       order, d_flags double[2] = the two counts summed over the ranks. */
+int toss_set_queue_order(toss_ctx *ctx, int mode);
+int toss_predict_cost(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
+                      int n_fixed, int n_man, int32_t *d_cost, uintptr_t stream);
+int toss_cost_order(toss_ctx *ctx, const int32_t *d_cost, int n, int32_t *d_order, uintptr_t stream);
+int toss_deal_rows(toss_ctx *ctx, const double *d_x, int n, int dim, const int32_t *d_order, int rank, int world,
+                   double *d_x_local, uintptr_t stream);
+int toss_pack_result(toss_ctx *ctx, const double *d_fitness_local, const toss_counters *d_counters_local, int n_local,
+                     int cap, double *d_send, uintptr_t stream);
+int toss_unpack_result(toss_ctx *ctx, const double *d_recv, const int32_t *d_order, int n, int world, int cap,
+                       double *d_fitness, double *d_flags, uintptr_t stream);
+
 /* Measures the FP64 FMA peak of the device (register-resident DFMA chains on every SM) in TFLOP/s;
  * the roofline denominator of bench.py (MEASURED_PEAKS.json has no FP64 entry). */
 int toss_measure_fp64_peak(toss_ctx *ctx, double *tflops_out);

@@ -129,16 +129,30 @@ def test_udp_is_picklable_and_validates_shapes():
         T.udp_initial_condition(a, fixed, lb, ub)
 
 
-def test_shard_bounds_cover_the_population():
-    from toss_b200.parallel import shard_bounds, champion
-    for n in (0, 1, 7, 16, 32768, 33001):
+def test_cost_slices_and_dealt_rows_cover_the_population():
+    """parallel.py: contiguous slices for the cost prediction (their concatenation IS the cost array), rows dealt
+    round-robin over the longest-first order: every row exactly once, shard sizes within one, predicted work balanced."""
+    from toss_b200.parallel import shard_bounds, champion, cost_order_host, deal_host, dealt_count
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 7, 16, 4099, 32768):
         for w in (1, 2, 3, 8):
             cuts = [shard_bounds(n, r, w) for r in range(w)]
+            cap = -(-n // w)
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(cuts[i][1] == cuts[i + 1][0] for i in range(w - 1))
-            sizes = [b - a for a, b in cuts]
-            assert max(sizes) - min(sizes) <= 1
-            assert sizes == [len(c) for c in np.array_split(np.arange(n), w)]
+            assert all(a == min(n, r * cap) for r, (a, b) in enumerate(cuts)) and all(b - a <= cap for a, b in cuts)
+            cost = rng.integers(200, 7000, size=n).astype(np.int32)
+            order = cost_order_host(cost)
+            assert sorted(order.tolist()) == list(range(n))
+            key = np.clip(cost >> 2, 0, 4095)
+            assert all(key[order[i]] > key[order[i + 1]] or (key[order[i]] == key[order[i + 1]] and order[i] < order[i + 1])
+                       for i in range(n - 1))
+            shards = [deal_host(order, r, w) for r in range(w)]
+            assert [len(s) for s in shards] == [dealt_count(n, r, w) for r in range(w)]
+            assert sorted(np.concatenate(shards).tolist()) == list(range(n))
+            if n >= 4096:   # the deal balances the predicted work to a fraction of one trajectory
+                work = [cost[s].sum() for s in shards]
+                assert max(work) - min(work) <= cost.max()
     assert champion(np.array([3.0, 1.0, 1.0, 2.0])) == (1, 1.0)
 
 
@@ -147,30 +161,44 @@ import os, sys
 import numpy as np
 import torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from toss_b200.parallel import shard_bounds, gather_population_fitness, champion, world
+from toss_b200.parallel import (shard_bounds, gather_costs_host, cost_order_host, deal_host, exchange_dealt, champion,
+                                world)
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
-n = 11
-truth = np.random.default_rng(4).normal(size=n)
-lo, hi = shard_bounds(n)
+rank = dist.get_rank()
 assert world() == (int(sys.argv[3]), 2)
-full = gather_population_fitness(truth[lo:hi].copy(), n)
+n = 11
+rng = np.random.default_rng(4)
+truth, cost = rng.normal(size=n), rng.integers(900, 6000, size=n).astype(np.int32)
+# (1) every rank predicts the cost of its contiguous slice, (2) all-gather, (3) same order everywhere
+lo, hi = shard_bounds(n)
+costs = gather_costs_host(cost[lo:hi], n)
+assert np.array_equal(costs, cost)
+order = cost_order_host(costs)
+rows = deal_host(order, rank, 2)
+# (4) "evaluate" the dealt rows, (5) exchange + un-deal: the full vector in population order on every rank
+full, (n_short, n_failed) = exchange_dealt(truth[rows], np.zeros(len(rows), np.int32), order, n)
 assert np.array_equal(full, truth), (full, truth)
+assert (n_short, n_failed) == (0, 0)
 assert champion(full) == (int(np.argmin(truth)), float(truth.min()))
-# a rank with an empty shard (n < world) still takes part in the collective
-one = gather_population_fitness(truth[:1] if dist.get_rank() == 0 else None, 1)
-assert one.shape == (1,) and one[0] == truth[0]
-# a failure seen by ONE rank (a trajectory out of knot capacity) reaches every rank with the same message
-full, flag = gather_population_fitness(truth[lo:hi].copy(), n, local_flag=(dist.get_rank() == 1), return_flag=True)
-assert flag is True and np.array_equal(full, truth)
-full, flag = gather_population_fitness(truth[lo:hi].copy(), n, return_flag=True)
-assert flag is False and np.array_equal(full, truth)
+# a rank with an empty shard (n < world) still takes part in the collectives
+o1 = cost_order_host(gather_costs_host(cost[:1] if shard_bounds(1)[1] > shard_bounds(1)[0] else cost[:0], 1))
+r1 = deal_host(o1, rank, 2)
+one, _ = exchange_dealt(truth[r1], None, o1, 1)
+assert one.shape == (1,) and one[0] == truth[0] and len(r1) == (1 if rank == 0 else 0)
+# failures seen by ONE rank (knot capacity: status 3; integrator: status 1 / 2) reach every rank as counts
+st = np.zeros(len(rows), np.int32)
+if rank == 1:
+    st[0], st[1] = 3, 2
+full, flags = exchange_dealt(truth[rows], st, order, n)
+assert flags == (1, 1) and np.array_equal(full, truth)
 dist.barrier(); dist.destroy_process_group()
-print("ok", lo, hi)
+print("ok", lo, hi, len(rows))
 '''
 
 
-def test_gather_over_two_gloo_ranks(tmp_path):
-    """SURVEY.md 8e: islands = contiguous slices, one all-gather of the fitness vector (gloo stands in for NCCL)."""
+def test_deal_and_gather_over_two_gloo_ranks(tmp_path):
+    """SURVEY.md 8e at world size 2 (gloo stands in for NCCL): cost slices -> all-gather -> common longest-first order ->
+    dealt rows -> all-gather of the fitness shards (+ failure counts) -> population order on every rank."""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
     port = str(29500 + os.getpid() % 2000)
@@ -178,7 +206,7 @@ def test_gather_over_two_gloo_ranks(tmp_path):
                               stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
-    assert outs[0].strip().endswith("ok 0 6") and outs[1].strip().endswith("ok 6 11")
+    assert outs[0].strip().endswith("ok 0 6 6") and outs[1].strip().endswith("ok 6 11 5")
 
 
 def test_grid_builder_input_assertions_are_the_reference_s():

@@ -59,7 +59,8 @@ EXPORTS = [
     "toss_rotate_points", "toss_workspace_layout", "toss_propagate", "toss_integrate", "toss_collision_verdict", "toss_num_samples", "toss_resample", "toss_dense_eval",
     "toss_fitness_eval", "toss_update_tensor", "toss_is_outside", "toss_population_fitness",
     "toss_population_fitness_host", "toss_measure_fp64_peak", "toss_launch_count", "toss_math_probe",
-    "toss_selftest_div_sqrt",
+    "toss_selftest_div_sqrt", "toss_set_queue_order", "toss_predict_cost", "toss_cost_order", "toss_deal_rows",
+    "toss_pack_result", "toss_unpack_result",
 ]
 
 _lib = None
@@ -118,6 +119,12 @@ def lib():
                                                c_double_p, C.POINTER(C.c_int32), vp, C.POINTER(C.c_int64)]
     L.toss_math_probe.argtypes = [vp, i32, vp, vp, i64, vp, vp, up]
     L.toss_selftest_div_sqrt.argtypes = [vp, i64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.toss_set_queue_order.argtypes = [vp, i32]
+    L.toss_predict_cost.argtypes = [vp, pp, vp, i32, i32, c_double_p, i32, i32, vp, up]
+    L.toss_cost_order.argtypes = [vp, vp, i32, vp, up]
+    L.toss_deal_rows.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, up]
+    L.toss_pack_result.argtypes = [vp, vp, vp, i32, i32, vp, up]
+    L.toss_unpack_result.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, up]
     L.toss_measure_fp64_peak.argtypes = [vp, c_double_p]
     L.toss_launch_count.restype = i64
     L.toss_launch_count.argtypes = [vp]
@@ -249,6 +256,16 @@ class Context:
             return a.to(device=self.device, dtype=dtype or t.float64).contiguous()
         return t.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
 
+    def to_device_pinned(self, a):
+        """host array -> CUDA tensor through a pinned staging buffer the context keeps (grows on demand)"""
+        t = self.torch
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if getattr(self, "_pin", None) is None or self._pin.numel() < a.size:
+            self._pin = t.empty(max(a.size, 1), dtype=t.float64).pin_memory()
+        stage = self._pin[:a.size].view(a.shape)
+        stage.copy_(t.from_numpy(a))
+        return stage.to(self.device, non_blocking=True)
+
     def launch_count(self) -> int:
         return int(lib().toss_launch_count(self.h))
 
@@ -291,6 +308,9 @@ class Context:
 
     # ---- K2 ---------------------------------------------------------------------------------------
     def workspace(self, pop: int, n_man: int, knot_cap: int):
+        """The propagation workspace for this shape.  ONE buffer is cached per context and reused by every later
+        propagate / integrate / population_fitness call of the same shape: a PropagationResult is a VIEW of it and is
+        overwritten by the next such call -- copy what must survive (`to_host()`) before propagating again."""
         key = (pop, n_man, knot_cap)
         if self._ws_key != key:
             L = WsLayout()
@@ -340,6 +360,41 @@ class Context:
                                    pos.data_ptr(), vel.data_ptr() if velocities else None, ts.data_ptr(),
                                    self._stream()))
         return pos, vel, ts
+
+    def resample_segments(self, params: TossParams, segments):
+        """get_trajectory_fixed_step for ONE trajectory given as a list of (t (n,), y (n,6), f (n,6)) knot arrays,
+        one entry per integration interval: the knots are packed into a one-trajectory propagation workspace and
+        toss_resample does the rest on the device (sample -> segment bookkeeping of trajectory_tools.py:46-74
+        included: csrc/fitness.cu build_seg_table).  Returns numpy positions (3,N), velocities (3,N), timesteps (N)."""
+        t = self.torch
+        n_seg = len(segments)
+        if n_seg < 1:
+            raise ValueError("resample_segments: no segments")
+        counts = [len(s[0]) for s in segments]
+        cap = max(4, sum(counts))
+        L = WsLayout()
+        _check(lib().toss_workspace_layout(1, n_seg - 1, cap, C.byref(L)))
+        ws = np.zeros(L.total_bytes, dtype=np.uint8)
+        kt = ws[L.knots_t:L.knots_t + 8 * cap].view(np.float64)
+        ky = ws[L.knots_y:L.knots_y + 48 * cap].view(np.float64).reshape(cap, 6)
+        kf = ws[L.knots_f:L.knots_f + 48 * cap].view(np.float64).reshape(cap, 6)
+        seg_start = ws[L.seg_start:L.seg_start + 4 * (n_seg + 1)].view(np.int32)
+        k = 0
+        for i, (st, sy, sf) in enumerate(segments):
+            n = counts[i]
+            seg_start[i] = k
+            kt[k:k + n], ky[k:k + n], kf[k:k + n] = st, sy, sf
+            k += n
+        seg_start[n_seg] = k
+        ws[L.n_seg:L.n_seg + 4].view(np.int32)[0] = n_seg
+        d_ws = t.from_numpy(ws).to(self.device)
+        N = self.num_samples(params)
+        out = t.empty((2, 3, max(N, 1)), dtype=t.float64, device=self.device)
+        ts = t.empty(max(N, 1), dtype=t.float64, device=self.device)
+        _check(lib().toss_resample(self.h, C.byref(params), d_ws.data_ptr(), 1, n_seg - 1, cap, out[0].data_ptr(),
+                                   out[1].data_ptr(), ts.data_ptr(), self._stream()))
+        h = out.cpu().numpy()
+        return h[0, :, :N], h[1, :, :N], ts.cpu().numpy()[:N]
 
     def dense_eval(self, kt, ky, kf, times):
         t = self.torch
@@ -405,6 +460,51 @@ class Context:
                                                   _dp(fit), coll.ctypes.data_as(C.POINTER(C.c_int32)), cnt.ctypes.data,
                                                   nv.ctypes.data_as(C.POINTER(C.c_int64))))
         return dict(fitness=fit, collision=coll, counters=cnt, n_visited=nv)
+
+    # ---- one population over several GPUs (include/toss_b200.h "one population over several GPUs") --------
+    def set_queue_order(self, pre_ordered: bool):
+        _check(lib().toss_set_queue_order(self.h, 1 if pre_ordered else 0))
+
+    def predict_cost(self, params: TossParams, xs, fixed, n_man: int, out=None):
+        """int32 cost key of every row of the CUDA tensor xs (pop, dim); `out` = int32 CUDA tensor of length >= pop"""
+        t = self.torch
+        pop, dim = xs.shape
+        fixed = _f64(fixed)
+        cost = t.empty(pop, dtype=t.int32, device=self.device) if out is None else out
+        if pop:
+            _check(lib().toss_predict_cost(self.h, C.byref(params), xs.data_ptr(), pop, dim,
+                                           _dp(fixed) if len(fixed) else None, len(fixed), n_man, cost.data_ptr(),
+                                           self._stream()))
+        return cost
+
+    def cost_order(self, cost):
+        order = self.torch.empty(len(cost), dtype=self.torch.int32, device=self.device)
+        _check(lib().toss_cost_order(self.h, cost.data_ptr(), len(cost), order.data_ptr(), self._stream()))
+        return order
+
+    def deal_rows(self, xs, order, rank: int, world: int):
+        n, dim = xs.shape
+        n_local = (n - rank + world - 1) // world
+        out = self.torch.empty((n_local, dim), dtype=self.torch.float64, device=self.device)
+        if n_local:
+            _check(lib().toss_deal_rows(self.h, xs.data_ptr(), n, dim, order.data_ptr(), rank, world, out.data_ptr(),
+                                        self._stream()))
+        return out
+
+    def pack_result(self, fitness, counters, n_local: int, cap: int):
+        send = self.torch.empty(cap + 2, dtype=self.torch.float64, device=self.device)
+        _check(lib().toss_pack_result(self.h, fitness.data_ptr() if n_local else None,
+                                      counters.data_ptr() if (n_local and counters is not None) else None, n_local, cap,
+                                      send.data_ptr(), self._stream()))
+        return send
+
+    def unpack_result(self, recv, order, n: int, world: int, cap: int):
+        t = self.torch
+        fit = t.empty(n, dtype=t.float64, device=self.device)
+        flags = t.empty(2, dtype=t.float64, device=self.device)
+        _check(lib().toss_unpack_result(self.h, recv.data_ptr(), order.data_ptr(), n, world, cap, fit.data_ptr(),
+                                        flags.data_ptr(), self._stream()))
+        return fit, flags
 
     def math_probe(self, fn: int, a, b=None):
         """tmath.cuh function `fn` over arrays (tests): numpy out, or (sin, cos) for fn 3"""

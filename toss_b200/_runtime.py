@@ -1,8 +1,11 @@
 """Host-side glue between the reference-style `args` DotMap and the device context.
 
 `args` is a plain (picklable) config object; the device context (mesh + voxel grid in HBM, ctypes and
-torch handles) lives HERE, in a per-process cache keyed by the mesh identity, so UDP objects can be
-deep-copied and pickled by pygmo (SURVEY.md 8b "Ownership") and re-attach lazily in a new process.
+torch handles) lives HERE, in a per-process cache with EXPLICIT keys -- (device, mesh identity) for everything that
+reads a mesh, ("bare", device) for the mesh-independent calls -- so UDP objects can be deep-copied and pickled by
+pygmo (SURVEY.md 8b "Ownership") and re-attach lazily in a new process.  A context holds one voxel grid at a time;
+`set_grid` (the only place that uploads one) compares the content and re-uploads when a caller with another grid
+comes along, so two UDPs that share a mesh but not a grid stay correct (each pays an 1 KB upload when they alternate).
 """
 from __future__ import annotations
 
@@ -43,16 +46,26 @@ def context_for_args(args, need_grid: bool = False) -> N.Context:
     return ctx
 
 
-def any_context() -> N.Context:
-    """A context for mesh-independent calls (fitness on given positions, rotations)."""
-    if _contexts:
-        return next(iter(_contexts.values()))
+def bare_context(device=None) -> N.Context:
+    """The context of the calls that need no mesh (fitness on given positions, rotations, voxel-grid updates): one
+    per device, created on first use, holding NO mesh and its own voxel grid.  It is never a mesh-bearing context
+    borrowed from the cache, so such calls cannot disturb the grid a UDP evaluates against (and vice versa)."""
     import torch
-    key = ("bare", torch.cuda.current_device() if torch.cuda.is_available() else 0)
-    ctx = N.Context(key[1])
-    ctx._grid_key = None
-    _contexts[key] = ctx
+    dev = torch.cuda.current_device() if device is None and torch.cuda.is_available() else (device or 0)
+    key = ("bare", dev)
+    ctx = _contexts.get(key)
+    if ctx is None:
+        ctx = N.Context(dev)
+        ctx._grid_key = None
+        _contexts[key] = ctx
     return ctx
+
+
+def release_contexts():
+    """Destroy every cached device context (tests; long-lived processes that switch meshes)."""
+    for ctx in list(_contexts.values()):
+        ctx.close()
+    _contexts.clear()
 
 
 def set_grid(ctx: N.Context, r, theta, phi, bool_tensor):

@@ -22,7 +22,6 @@ int toss_ctx_create(int device, toss_ctx **out)
     int n = 0;
     TOSS_CHECK_CUDA(cudaGetDeviceCount(&n));
     TOSS_REQUIRE(device >= 0 && device < n, "toss_ctx_create: no such CUDA device");
-    TOSS_CHECK_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     TOSS_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
     TOSS_REQUIRE(prop.major == 10, "toss_ctx_create: this library is built for sm_100a (B200) only");
@@ -60,10 +59,12 @@ static void free_grid(toss_ctx *c)
 int toss_ctx_destroy(toss_ctx *ctx)
 {
     if (!ctx) return 0;
-    cudaSetDevice(ctx->device);
+    DeviceScope dev(ctx->device);
     free_mesh(ctx);
     free_grid(ctx);
     cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_tensor_scratch);
+    cudaFree(ctx->queue_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
     return 0;
@@ -96,7 +97,7 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
 {
     TOSS_REQUIRE(ctx && h_verts && h_faces, "toss_mesh_upload: NULL argument");
     TOSS_REQUIRE(V >= 4 && F >= 4, "toss_mesh_upload: a closed mesh needs at least 4 vertices and 4 faces");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     for (int i = 0; i < 3 * F; ++i)
         TOSS_REQUIRE(h_faces[i] >= 0 && h_faces[i] < V, "toss_mesh_upload: face index out of range");
     // the pairing and the per-pair constants (pairs.cu)
@@ -239,7 +240,7 @@ int toss_grid_upload(toss_ctx *ctx, const double *h_r, int nr, const double *h_t
     TOSS_REQUIRE(ctx && h_r && h_theta && h_phi && h_bool_tensor, "toss_grid_upload: NULL argument");
     TOSS_REQUIRE(nr >= 1 && nth >= 1 && nph >= 1, "toss_grid_upload: empty grid axis");
     TOSS_REQUIRE((long long)nr * nth * nph < (1LL << 31), "toss_grid_upload: grid too large");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     free_grid(ctx);
     ctx->nr = nr;
     ctx->nth = nth;
@@ -261,7 +262,7 @@ int toss_gravity_eval(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_a
 {
     TOSS_REQUIRE(ctx != nullptr, "toss_gravity_eval: NULL context");
     TOSS_REQUIRE(n == 0 || (d_pts && d_acc), "toss_gravity_eval: NULL buffer");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_gravity(ctx, d_pts, n, d_acc, d_pot, (cudaStream_t)stream);
 }
 
@@ -269,7 +270,7 @@ int toss_compute_motion(toss_ctx *ctx, const toss_params *p, const double *d_t, 
                         double *d_out, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && p, "toss_compute_motion: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_compute_motion(ctx, p, d_t, d_y, n, d_out, (cudaStream_t)stream);
 }
 
@@ -283,7 +284,7 @@ int toss_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int p
                    int n_fixed, int n_man, void *d_workspace, int knot_cap, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && p && d_workspace && (d_x || dim == 0), "toss_propagate: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     // the stepper ray-casts every event point while it sweeps the faces: the verdict is already in the workspace
     return launch_propagate(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_workspace, knot_cap,
                             (cudaStream_t)stream);
@@ -293,7 +294,7 @@ int toss_integrate(toss_ctx *ctx, const toss_params *p, const double *d_x, int p
                    int n_fixed, int n_man, void *d_workspace, int knot_cap, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && p && d_workspace && (d_x || dim == 0), "toss_integrate: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_propagate(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_workspace, knot_cap, (cudaStream_t)stream);
 }
 
@@ -301,7 +302,7 @@ int toss_collision_verdict(toss_ctx *ctx, const toss_params *p, void *d_workspac
                            uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && p && d_workspace, "toss_collision_verdict: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_collision(ctx, p, d_workspace, pop, n_man, knot_cap, (cudaStream_t)stream);
 }
 
@@ -309,7 +310,7 @@ int toss_rotate_points(toss_ctx *ctx, const double *h_axis3, double spin_velocit
                        const double *d_x, int64_t n, double *d_out, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && h_axis3 && (n == 0 || (d_t && d_x && d_out)), "toss_rotate_points: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_rotate_points(ctx, h_axis3, spin_velocity, d_t, d_x, n, d_out, (cudaStream_t)stream);
 }
 
@@ -323,7 +324,7 @@ int toss_resample(toss_ctx *ctx, const toss_params *p, const void *d_workspace, 
                   double *d_pos, double *d_vel, double *d_ts, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && p && d_workspace && d_pos, "toss_resample: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_resample(ctx, p, d_workspace, pop, n_man, knot_cap, d_pos, d_vel, d_ts, (cudaStream_t)stream);
 }
 
@@ -331,7 +332,7 @@ int toss_dense_eval(toss_ctx *ctx, const double *d_kt, const double *d_ky, const
                     const double *d_t, int64_t nt, double *d_out, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && d_kt && d_ky && d_kf && d_t && d_out, "toss_dense_eval: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_dense_eval(ctx, d_kt, d_ky, d_kf, n_knots, d_t, nt, d_out, (cudaStream_t)stream);
 }
 
@@ -339,7 +340,7 @@ int toss_fitness_eval(toss_ctx *ctx, int fn, const toss_params *p, const double 
                       const double *d_ts, double *d_fitness, int64_t *d_n_visited, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && p && d_pos && d_ts && d_fitness, "toss_fitness_eval: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_fitness_positions(ctx, fn, p, d_pos, batch, N, d_ts, d_fitness, d_n_visited, nullptr,
                                     (cudaStream_t)stream);
 }
@@ -349,14 +350,21 @@ int toss_update_tensor(toss_ctx *ctx, const toss_params *p, const double *d_pos,
 {
     TOSS_REQUIRE(ctx && p && d_pos && d_ts, "toss_update_tensor: NULL argument");
     TOSS_REQUIRE(ctx->d_grid != nullptr, "toss_update_tensor: no voxel grid uploaded");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     const long long nvox = (long long)ctx->nr * ctx->nth * ctx->nph;
     const size_t nw = (size_t)((nvox + 31) / 32);
-    double *d_fit = nullptr;
-    uint32_t *d_bits = nullptr;
-    TOSS_CHECK_CUDA(cudaMalloc(&d_fit, 8));
-    TOSS_CHECK_CUDA(cudaMalloc(&d_bits, nw * 4));
+    // [fitness (8 B, unused) | visited bits] in a small buffer the context keeps (no allocation per call)
+    if (ctx->tensor_scratch_bytes < 256 + nw * 4) {
+        cudaFree(ctx->d_tensor_scratch);
+        ctx->d_tensor_scratch = nullptr;
+        ctx->tensor_scratch_bytes = 0;
+        TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_tensor_scratch, 256 + nw * 4));
+        ctx->tensor_scratch_bytes = 256 + nw * 4;
+    }
+    double *d_fit = static_cast<double *>(ctx->d_tensor_scratch);
+    uint32_t *d_bits = reinterpret_cast<uint32_t *>(static_cast<unsigned char *>(ctx->d_tensor_scratch) + 256);
+    NvtxRange nv("toss:update_tensor");
     int rc = launch_fitness_positions(ctx, 8, p, d_pos, 1, N, d_ts, d_fit, nullptr, d_bits, st);
     std::vector<uint32_t> bits(nw);
     if (!rc) {
@@ -367,8 +375,6 @@ int toss_update_tensor(toss_ctx *ctx, const toss_params *p, const double *d_pos,
             rc = 1;
         }
     }
-    cudaFree(d_fit);
-    cudaFree(d_bits);
     if (rc) return rc;
     for (long long b = 0; b < nvox; ++b) ctx->h_bool[b] = (bits[b >> 5] >> (b & 31)) & 1u;
     if (h_bool_tensor_out) memcpy(h_bool_tensor_out, ctx->h_bool, (size_t)nvox);
@@ -378,7 +384,7 @@ int toss_update_tensor(toss_ctx *ctx, const toss_params *p, const double *d_pos,
 int toss_is_outside(toss_ctx *ctx, const double *d_pts, int64_t n, uint8_t *d_out, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && (n == 0 || (d_pts && d_out)), "toss_is_outside: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_is_outside(ctx, d_pts, n, d_out, (cudaStream_t)stream);
 }
 
@@ -388,9 +394,11 @@ int toss_population_fitness(toss_ctx *ctx, const toss_params *p, const double *d
                             uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && p && d_workspace && d_fitness, "toss_population_fitness: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     cudaStream_t st = (cudaStream_t)stream;
+    NvtxRange nv("toss:population_fitness");
     if (int rc = launch_propagate(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_workspace, knot_cap, st)) return rc;
+    NvtxRange nv2("toss:K3+K4 resample+fitness");
     return launch_fitness_knots(ctx, p, d_workspace, pop, n_man, knot_cap, d_fitness, d_collision, d_counters,
                                 d_n_visited, st);
 }
@@ -401,7 +409,7 @@ int toss_population_fitness_host(toss_ctx *ctx, const toss_params *p, const doub
 {
     TOSS_REQUIRE(ctx && p && h_fitness && (h_x || dim == 0), "toss_population_fitness_host: NULL argument");
     TOSS_REQUIRE(pop > 0, "toss_population_fitness_host: empty population");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     toss_ws_layout L;
     toss_workspace_layout_impl(pop, n_man, knot_cap, &L);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -454,27 +462,74 @@ int toss_population_fitness_host(toss_ctx *ctx, const toss_params *p, const doub
     return 0;
 }
 
+// ---- multi-GPU plumbing (sharding.cu, stepper.cu) ------------------------------------------------------
+int toss_set_queue_order(toss_ctx *ctx, int mode)
+{
+    TOSS_REQUIRE(ctx && (mode == 0 || mode == 1), "toss_set_queue_order: mode must be 0 (auto) or 1 (rows pre-ordered)");
+    ctx->queue_order_mode = mode;
+    return 0;
+}
+
+int toss_predict_cost(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
+                      int n_fixed, int n_man, int32_t *d_cost, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx && p && d_cost && (d_x || dim == 0), "toss_predict_cost: NULL argument");
+    TOSS_ENTER(ctx);
+    return launch_predict_cost(ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, d_cost, (cudaStream_t)stream);
+}
+
+int toss_cost_order(toss_ctx *ctx, const int32_t *d_cost, int n, int32_t *d_order, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx != nullptr, "toss_cost_order: NULL context");
+    TOSS_ENTER(ctx);
+    return launch_cost_order(ctx, d_cost, n, d_order, (cudaStream_t)stream);
+}
+
+int toss_deal_rows(toss_ctx *ctx, const double *d_x, int n, int dim, const int32_t *d_order, int rank, int world,
+                   double *d_x_local, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx != nullptr, "toss_deal_rows: NULL context");
+    TOSS_ENTER(ctx);
+    return launch_deal_rows(ctx, d_x, n, dim, d_order, rank, world, d_x_local, (cudaStream_t)stream);
+}
+
+int toss_pack_result(toss_ctx *ctx, const double *d_fitness_local, const toss_counters *d_counters_local, int n_local,
+                     int cap, double *d_send, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx != nullptr, "toss_pack_result: NULL context");
+    TOSS_ENTER(ctx);
+    return launch_pack_result(ctx, d_fitness_local, d_counters_local, n_local, cap, d_send, (cudaStream_t)stream);
+}
+
+int toss_unpack_result(toss_ctx *ctx, const double *d_recv, const int32_t *d_order, int n, int world, int cap,
+                       double *d_fitness, double *d_flags, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx != nullptr, "toss_unpack_result: NULL context");
+    TOSS_ENTER(ctx);
+    return launch_unpack_result(ctx, d_recv, d_order, n, world, cap, d_fitness, d_flags, (cudaStream_t)stream);
+}
+
 int toss_math_probe(toss_ctx *ctx, int fn, const double *d_a, const double *d_b, int64_t n, double *d_out,
                     double *d_out2, uintptr_t stream)
 {
     TOSS_REQUIRE(ctx && (n == 0 || (d_a && d_out)), "toss_math_probe: NULL argument");
     TOSS_REQUIRE(fn >= 0 && fn <= 14, "toss_math_probe: unknown function id");
     TOSS_REQUIRE(!(fn == 2 || fn == 7) || d_b, "toss_math_probe: this function needs a second operand");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_math_probe(ctx, fn, d_a, d_b, n, d_out, d_out2, (cudaStream_t)stream);
 }
 
 int toss_selftest_div_sqrt(toss_ctx *ctx, int64_t samples, int64_t *bad_div, int64_t *bad_sqrt)
 {
     TOSS_REQUIRE(ctx && bad_div && bad_sqrt && samples > 0, "toss_selftest_div_sqrt: bad argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_div_sqrt_selftest(ctx, samples, bad_div, bad_sqrt);
 }
 
 int toss_measure_fp64_peak(toss_ctx *ctx, double *tflops_out)
 {
     TOSS_REQUIRE(ctx && tflops_out, "toss_measure_fp64_peak: NULL argument");
-    TOSS_CHECK_CUDA(cudaSetDevice(ctx->device));
+    TOSS_ENTER(ctx);
     return launch_fp64_peak(ctx, tflops_out);
 }
 

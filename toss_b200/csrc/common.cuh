@@ -81,12 +81,44 @@ struct toss_ctx {
     // internal buffers of the *_host entry points
     void *d_scratch = nullptr;
     size_t scratch_bytes = 0;
+    void *d_tensor_scratch = nullptr;   // toss_update_tensor: [fitness | visited bits]
+    size_t tensor_scratch_bytes = 0;
     void *h_pinned = nullptr;
     size_t pinned_bytes = 0;
     int64_t launches = 0;
+    int queue_order_mode = 0;        // 0: the launcher orders the work queue itself (proxy run); 1: rows are pre-ordered
+    int32_t *queue_scratch = nullptr;   // 256 B: work-queue cursor of toss_predict_cost's proxy run
 };
 
 void toss_set_error(const std::string &msg);
+
+// Every ABI entry point runs on the context's device and leaves the caller's current device as it found it
+// (a Context on cuda:1 must not silently change torch's current device).
+struct DeviceScope {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceScope(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;   // nothing to restore
+    }
+    ~DeviceScope()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define TOSS_ENTER(ctx)                                                                                \
+    DeviceScope _toss_dev((ctx)->device);                                                              \
+    TOSS_CHECK_CUDA(_toss_dev.err)
+
+// NVTX ranges around the phases of a population evaluation (proxy run / queue sort / stepper / resample + fitness):
+// visible to nsys / ncu --nvtx, free when no tool is attached (header-only NVTX v3).
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define TOSS_CHECK_CUDA(expr)                                                                          \
     do {                                                                                               \
@@ -177,6 +209,15 @@ int launch_compute_motion(toss_ctx *ctx, const toss_params *p, const double *d_t
                           double *d_out, cudaStream_t st);
 int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
                      int n_fixed, int n_man, void *d_ws, int knot_cap, cudaStream_t st);
+int launch_predict_cost(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
+                        int n_fixed, int n_man, int32_t *d_cost, cudaStream_t st);
+int launch_cost_order(toss_ctx *ctx, const int32_t *d_cost, int n, int32_t *d_order, cudaStream_t st);
+int launch_deal_rows(toss_ctx *ctx, const double *d_x, int n, int dim, const int32_t *d_order, int rank, int world,
+                     double *d_x_local, cudaStream_t st);
+int launch_pack_result(toss_ctx *ctx, const double *d_fit, const toss_counters *d_cnt, int n_local, int cap,
+                       double *d_send, cudaStream_t st);
+int launch_unpack_result(toss_ctx *ctx, const double *d_recv, const int32_t *d_order, int n, int world, int cap,
+                         double *d_fitness, double *d_flags, cudaStream_t st);
 int launch_collision(toss_ctx *ctx, const toss_params *p, void *d_ws, int pop, int n_man, int knot_cap,
                      cudaStream_t st);
 int launch_resample(toss_ctx *ctx, const toss_params *p, const void *d_ws, int pop, int n_man, int knot_cap,

@@ -19,6 +19,7 @@
 //             run at most two tiles ahead), so every byte fetched from L2 is used by 16 trajectories.
 //             There is no CTA-wide barrier after start-up: warps retire from the ring with arrive_drop.
 #include <stdlib.h>
+#include <string.h>
 
 #include "gravity.cuh"
 
@@ -738,15 +739,19 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 // count equals the real one for most trajectories, r = 0.96 overall) at ~5 % of the real cost; the counts are the sort
 // key (longest first).  The order only schedules: results are written by trajectory index and do not depend on it.
 // ------------------------------------------------------------------------------------------------
-// one block: counting sort of the predicted costs, longest first (order within a bin is irrelevant)
-__global__ void __launch_bounds__(1024) cost_sort_kernel(const int32_t *__restrict__ cost, int pop,
-                                                         int32_t *__restrict__ order)
+// One block: STABLE counting sort of the predicted costs, longest first, ties in index order -- a pure function of the
+// cost array, so every rank of a multi-GPU job derives the same order from the same (all-gathered) costs and the
+// dealt shards are consistent (parallel.py).  Chunks of 1024 elements in index order; inside a chunk the warps take
+// their turns in warp order, inside a warp equal bins are ranked by lane (match_any): no atomics on the output.
+__global__ void __launch_bounds__(1024) cost_order_kernel(const int32_t *__restrict__ cost, int n,
+                                                          int32_t *__restrict__ order)
 {
     __shared__ int hist[4096];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int b = threadIdx.x; b < 4096; b += blockDim.x) hist[b] = 0;
     __syncthreads();
     auto key = [](int c) { c >>= 2; return c < 0 ? 0 : (c > 4095 ? 4095 : c); };
-    for (int i = threadIdx.x; i < pop; i += blockDim.x) atomicAdd(&hist[key(cost[i])], 1);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[key(cost[i])], 1);
     __syncthreads();
     if (threadIdx.x == 0) {
         int run = 0;
@@ -757,7 +762,24 @@ __global__ void __launch_bounds__(1024) cost_sort_kernel(const int32_t *__restri
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < pop; i += blockDim.x) order[atomicAdd(&hist[key(cost[i])], 1)] = i;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        const bool valid = i < n;
+        const int b = valid ? key(cost[i]) : -1 - lane;            // invalid lanes match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        const int rank_in_warp = __popc(peers & ((1u << lane) - 1u)), cnt = __popc(peers);
+        const bool leader = rank_in_warp == 0;
+        int off = 0;
+        for (int w = 0; w < 32; ++w) {
+            if (wid == w && valid && leader) {
+                off = hist[b];
+                hist[b] = off + cnt;
+            }
+            __syncthreads();
+        }
+        off = __shfl_sync(0xffffffffu, off, __ffs(peers) - 1);
+        if (valid) order[off + rank_in_warp] = i;
+    }
 }
 
 int toss_workspace_layout_impl(int pop, int n_man, int knot_cap, toss_ws_layout *out)
@@ -777,19 +799,22 @@ int toss_workspace_layout_impl(int pop, int n_man, int knot_cap, toss_ws_layout 
     return 0;
 }
 
-int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
-                     int n_fixed, int n_man, void *d_ws, int knot_cap, cudaStream_t st)
+static size_t stepper_state_bytes(int n_man)
 {
-    TOSS_REQUIRE(ctx && ctx->d_pair_soa, "toss_propagate: no mesh uploaded");
-    TOSS_REQUIRE(pop > 0 && dim >= 0 && n_fixed >= 0 && n_fixed <= 7, "toss_propagate: bad population shape");
-    TOSS_REQUIRE(n_man >= 0 && n_man <= 64, "toss_propagate: number_of_maneuvers must be in [0, 64]");
-    TOSS_REQUIRE(n_fixed + dim == 7 + 5 * n_man, "toss_propagate: n_fixed + dim != 7 + 5*number_of_maneuvers");
-    TOSS_REQUIRE(knot_cap >= 4, "toss_propagate: knot capacity too small");
-    TOSS_REQUIRE((int32_t)p->final_time > (int32_t)p->start_time, "toss_propagate: final_time <= start_time");
-    toss_ws_layout L;
-    toss_workspace_layout_impl(pop, n_man, knot_cap, &L);
-    unsigned char *ws = static_cast<unsigned char *>(d_ws);
-    StepArgs a;
+    return (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 + (size_t)kTeamBufs * kTeamBufDoubles * 8 +
+           (size_t)kK2Warps * kScratchDoubles * 8;
+}
+
+// the part of StepArgs that does not depend on a workspace
+static int fill_step_args(StepArgs &a, toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim,
+                          const double *h_fixed, int n_fixed, int n_man, const char *who)
+{
+    TOSS_REQUIRE(ctx && ctx->d_pair_soa, std::string(who) + ": no mesh uploaded");
+    TOSS_REQUIRE(pop > 0 && dim >= 0 && n_fixed >= 0 && n_fixed <= 7, std::string(who) + ": bad population shape");
+    TOSS_REQUIRE(n_man >= 0 && n_man <= 64, std::string(who) + ": number_of_maneuvers must be in [0, 64]");
+    TOSS_REQUIRE(n_fixed + dim == 7 + 5 * n_man, std::string(who) + ": n_fixed + dim != 7 + 5*number_of_maneuvers");
+    TOSS_REQUIRE((int32_t)p->final_time > (int32_t)p->start_time, std::string(who) + ": final_time <= start_time");
+    memset(&a, 0, sizeof(a));
     a.p = *p;
     a.axis = unit_axis_host(p->spin_axis);
     a.Grho = ctx->Grho;
@@ -805,8 +830,77 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     a.dim = dim;
     a.n_fixed = n_fixed;
     a.n_man = n_man;
-    a.knot_cap = knot_cap;
     for (int i = 0; i < 8; ++i) a.fixed[i] = (i < n_fixed && h_fixed) ? h_fixed[i] : 0.0;
+    return 0;
+}
+
+// The PROXY run: predicted RHS count of every trajectory of `a` (a.queue must point at a zeroed cursor).  It only has
+// to RANK the trajectories by length: it runs at a loose tolerance (the step count of an 8th-order method scales
+// like tol^(-1/8) for every trajectory alike: 7.5x fewer steps at 1e-5 than at 1e-12).
+static int launch_proxy(toss_ctx *ctx, const StepArgs &a, int32_t *d_cost, cudaStream_t st)
+{
+    StepArgs px = a;
+    px.order = nullptr;
+    px.pair_soa = ctx->d_mascons;
+    px.proxy_n = ctx->n_mascons;
+    px.proxy_soft2 = ctx->mascon_soft2;
+    px.proxy_cost = d_cost;
+    double ptol = 1e-5;
+    if (const char *e = getenv("TOSS_B200_PROXY_TOL")) ptol = atof(e) > 0.0 ? atof(e) : ptol;   // developer override
+    if (px.p.rtol < ptol) px.p.rtol = ptol;
+    if (px.p.atol < ptol) px.p.atol = ptol;
+    const size_t psmem = (size_t)4 * ctx->n_mascons * 8 + stepper_state_bytes(a.n_man);
+    const int pctas = a.pop < K2_MINBLOCKS * ctx->sm_count ? a.pop : K2_MINBLOCKS * ctx->sm_count;
+    px.first_round = a.pop / pctas < kK2Warps ? a.pop / pctas : kK2Warps;
+    px.first_extra = a.pop / pctas < kK2Warps ? a.pop % pctas : 0;
+    TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)psmem));
+    stepper_kernel<false, 1, true><<<pctas, kK2Threads, psmem, st>>>(px);
+    ctx->launches++;
+    TOSS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// whether the proxy run pays: the mesh must be large enough that a mascon evaluation is cheap next to a real one
+static bool proxy_pays(const toss_ctx *ctx) { return ctx->F >= 1000 && ctx->n_mascons > 0; }
+
+// toss_predict_cost: the cost key of every chromosome (0 everywhere when the proxy would not pay: any order is as
+// good as another then).  d_scratch_queue: >= 256 bytes of device memory for the proxy's work-queue cursor.
+int launch_predict_cost(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
+                        int n_fixed, int n_man, int32_t *d_cost, cudaStream_t st)
+{
+    StepArgs a;
+    if (int rc = fill_step_args(a, ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, "toss_predict_cost")) return rc;
+    if (!proxy_pays(ctx)) {
+        TOSS_CHECK_CUDA(cudaMemsetAsync(d_cost, 0, sizeof(int32_t) * (size_t)pop, st));
+        return 0;
+    }
+    if (ctx->queue_scratch == nullptr) TOSS_CHECK_CUDA(cudaMalloc(&ctx->queue_scratch, 256));
+    a.queue = ctx->queue_scratch;
+    TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
+    NvtxRange nv("toss:proxy run (cost prediction)");
+    return launch_proxy(ctx, a, d_cost, st);
+}
+
+int launch_cost_order(toss_ctx *ctx, const int32_t *d_cost, int n, int32_t *d_order, cudaStream_t st)
+{
+    TOSS_REQUIRE(d_cost && d_order && n > 0, "toss_cost_order: bad argument");
+    cost_order_kernel<<<1, 1024, 0, st>>>(d_cost, n, d_order);
+    ctx->launches++;
+    TOSS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
+                     int n_fixed, int n_man, void *d_ws, int knot_cap, cudaStream_t st)
+{
+    StepArgs a;
+    if (int rc = fill_step_args(a, ctx, p, d_x, pop, dim, h_fixed, n_fixed, n_man, "toss_propagate")) return rc;
+    TOSS_REQUIRE(knot_cap >= 4, "toss_propagate: knot capacity too small");
+    toss_ws_layout L;
+    toss_workspace_layout_impl(pop, n_man, knot_cap, &L);
+    unsigned char *ws = static_cast<unsigned char *>(d_ws);
+    a.knot_cap = knot_cap;
     a.knots_t = reinterpret_cast<double *>(ws + L.knots_t);
     a.knots_y = reinterpret_cast<double *>(ws + L.knots_y);
     a.knots_f = reinterpret_cast<double *>(ws + L.knots_f);
@@ -830,43 +924,23 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     else if (rows < 3 && team > 2) team = 2;
     if (const char *e = getenv("TOSS_B200_TEAM")) team = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1);   // developer override
     // longest-first queue order when trajectories queue for warps (otherwise order is irrelevant) and the mesh is
-    // large enough that the proxy run is cheap next to the real one (lp pop 32768: 1292 -> 1220 ms)
-    bool lpt = (long long)pop * team > slots && ctx->F >= 1000 && ctx->n_mascons > 0;
-    if (const char *e = getenv("TOSS_B200_LPT")) lpt = atoi(e) != 0 && ctx->n_mascons > 0;
+    // large enough that the proxy run is cheap next to the real one (lp pop 32768: 1292 -> 1220 ms).  A caller that
+    // has ordered the rows itself (the multi-GPU deal of parallel.py hands every rank a longest-first shard) says so
+    // with toss_set_queue_order(ctx, 1): the queue then runs in row order.
+    bool lpt = ctx->queue_order_mode == 0 && (long long)pop * team > slots && proxy_pays(ctx);
+    if (const char *e = getenv("TOSS_B200_LPT")) lpt = atoi(e) != 0 && ctx->n_mascons > 0 && ctx->queue_order_mode == 0;
     a.order = nullptr;
-    a.proxy_n = 0;
-    a.proxy_soft2 = 0.0;
-    a.proxy_cost = nullptr;
     if (lpt) {
+        NvtxRange nv("toss:proxy run + queue sort (longest first)");
         int32_t *order = a.queue + 4, *cost = order + pop;
-        StepArgs px = a;
-        px.pair_soa = ctx->d_mascons;
-        px.proxy_n = ctx->n_mascons;
-        px.proxy_soft2 = ctx->mascon_soft2;
-        px.proxy_cost = cost;
-        // The proxy only has to RANK the trajectories by length: it runs at a loose tolerance (the step count of an
-        // 8th-order method scales like tol^(-1/8) for every trajectory alike: 7.5x fewer steps at 1e-5 than at 1e-12).
-        double ptol = 1e-5;
-        if (const char *e = getenv("TOSS_B200_PROXY_TOL")) ptol = atof(e) > 0.0 ? atof(e) : ptol;   // developer override
-        if (px.p.rtol < ptol) px.p.rtol = ptol;
-        if (px.p.atol < ptol) px.p.atol = ptol;
-        const size_t psmem = (size_t)4 * ctx->n_mascons * 8 + (size_t)kK2Warps * warp_state_doubles(n_man) * 8 +
-                             kK2BarSlots * 8 + (size_t)kTeamBufs * kTeamBufDoubles * 8 +
-                             (size_t)kK2Warps * kScratchDoubles * 8;
-        const int pctas = pop < K2_MINBLOCKS * ctx->sm_count ? pop : K2_MINBLOCKS * ctx->sm_count;
-        px.first_round = pop / pctas < kK2Warps ? pop / pctas : kK2Warps;
-        px.first_extra = pop / pctas < kK2Warps ? pop % pctas : 0;
-        TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)psmem));
-        stepper_kernel<false, 1, true><<<pctas, kK2Threads, psmem, st>>>(px);
-        cost_sort_kernel<<<1, 1024, 0, st>>>(cost, pop, order);
+        if (int rc = launch_proxy(ctx, a, cost, st)) return rc;
+        if (int rc = launch_cost_order(ctx, cost, pop, order, st)) return rc;
         TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 16, st));
-        ctx->launches += 2;
         a.order = order;
     }
 
-    const size_t state_bytes = (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 +
-                               (size_t)kTeamBufs * kTeamBufDoubles * 8 + (size_t)kK2Warps * kScratchDoubles * 8;
+    NvtxRange nv_k2("toss:K2 stepper");
+    const size_t state_bytes = stepper_state_bytes(n_man);
     const size_t resident_bytes = (size_t)2 * kPairSlots * ctx->Ppad32 * 8 + state_bytes;
     const size_t stream_bytes = (size_t)kK2Stages * kPairTileBytes + state_bytes;
     const bool resident = resident_bytes <= (size_t)(200 / K2_MINBLOCKS) * 1024;   // every CTA on an SM keeps its own copy

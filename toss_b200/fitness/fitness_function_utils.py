@@ -8,7 +8,7 @@ from typing import Union
 
 import numpy as np
 
-from .._runtime import any_context, default_params, set_grid
+from .._runtime import bare_context, default_params, set_grid
 
 
 def _positions_3xN(positions):
@@ -30,7 +30,7 @@ def compute_space_coverage(number_of_spacecrafts: int, spin_axis: np.ndarray, sp
                            bool_tensor: np.ndarray) -> float:
     """ratio of visited grid points + sum of 1/r over them (:54-162).  `positions` is (3,N), or (3,) for a
     single position rotated with timesteps[0] (:84-93).  `velocities` is unused, as in the reference."""
-    ctx = any_context()
+    ctx = bare_context()
     set_grid(ctx, r, theta, phi, bool_tensor)
     single = np.asarray(positions).ndim == 1
     pos = _positions_3xN(positions)
@@ -44,7 +44,7 @@ def update_spherical_tensor_grid(number_of_spacecrafts: int, spin_axis: np.ndarr
                                  radius_min: float, radius_max: float, r: np.ndarray, theta: np.ndarray,
                                  phi: np.ndarray, bool_tensor: np.ndarray) -> np.ndarray:
     """bool_tensor OR the voxels visited by `positions` (:165-228); returns the new tensor."""
-    ctx = any_context()
+    ctx = bare_context()
     set_grid(ctx, r, theta, phi, bool_tensor)
     pos = _positions_3xN(positions)
     ts = np.ascontiguousarray(np.atleast_1d(np.asarray(timesteps, dtype=np.float64)))
@@ -98,7 +98,7 @@ def estimate_covered_volume(positions: np.ndarray) -> float:
     pos = _positions_3xN(positions)
     if pos.shape[1] < 2:      # the reference fails on `sphere_radii[0] = sphere_radii[1]` (:30-31)
         raise IndexError("index 1 is out of bounds for axis 0 with size 1")
-    ctx = any_context()
+    ctx = bare_context()
     p = default_params(total_measurable_volume=1.0)
     if ctx.grid_shape is None:
         ctx.upload_grid([1.0], [0.0], [0.0], np.zeros((1, 1, 1), dtype=np.uint8))

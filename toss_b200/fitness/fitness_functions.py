@@ -2,7 +2,7 @@
 every value is computed by the K4 kernel through toss_fitness_eval."""
 import numpy as np
 
-from .._runtime import any_context, default_params, params_from_args, set_grid
+from .._runtime import bare_context, default_params, params_from_args, set_grid
 from .fitness_function_enums import FitnessFunctions
 from .fitness_function_utils import _positions_3xN, compute_space_coverage
 
@@ -13,9 +13,9 @@ def _eval(fn: int, p, positions, timesteps=None) -> float:
         # estimate_covered_volume needs two samples: the reference fails on `sphere_radii[0] = sphere_radii[1]`
         # (fitness_function_utils.py:30-31) -- same exception type here
         raise IndexError("index 1 is out of bounds for axis 0 with size 1")
-    ctx = any_context()
+    ctx = bare_context()
     if ctx.grid_shape is None:   # ids 1..7 never touch the grid, but the kernel signature carries one
-        ctx.upload_grid([1.0], [0.0], [0.0], np.zeros((1, 1, 1), dtype=np.uint8))
+        set_grid(ctx, [1.0], [0.0], [0.0], np.zeros((1, 1, 1), dtype=np.uint8))
     ts = np.zeros(pos.shape[1]) if timesteps is None else np.ascontiguousarray(timesteps, dtype=np.float64)
     return float(ctx.fitness(fn, p, pos, ts).cpu()[0])
 
@@ -26,7 +26,7 @@ def get_fitness(chosen_fitness_function: FitnessFunctions, args, positions: np.n
     cfg) to the coverage functions -- reproduced by params_from_args."""
     fn = FitnessFunctions(chosen_fitness_function).value
     p = params_from_args(args)
-    ctx = any_context()
+    ctx = bare_context()
     if fn in (8, 9):
         set_grid(ctx, args.problem.tensor_grid_r, args.problem.tensor_grid_theta, args.problem.tensor_grid_phi,
                  args.problem.bool_tensor)
@@ -93,7 +93,7 @@ def covered_space_close_distance_penalty_far_distance_penalty(number_of_spacecra
                                                               r: np.ndarray, theta: np.ndarray, phi: np.ndarray,
                                                               bool_tensor: np.ndarray) -> float:
     """close + far - coverage (:198-227)"""
-    ctx = any_context()
+    ctx = bare_context()
     set_grid(ctx, r, theta, phi, bool_tensor)
     p = default_params(number_of_spacecrafts=int(number_of_spacecrafts),
                        spin_axis=np.asarray(spin_axis, dtype=np.float64), spin_velocity=float(spin_velocity),

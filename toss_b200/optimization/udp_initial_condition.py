@@ -11,8 +11,13 @@ from typing import Union
 
 import numpy as np
 
+from .. import parallel as P
 from .._runtime import context_for_args, params_from_args
-from ..parallel import gather_population_fitness, shard_bounds
+
+
+def ctx_counters_dtype():
+    from .._native import COUNTERS_DTYPE
+    return COUNTERS_DTYPE
 
 
 class udp_initial_condition:
@@ -45,6 +50,11 @@ class udp_initial_condition:
         self.args.problem.number_of_spacecraft = 1   # (sic) the reference sets this unused singular key (:103)
         self.knot_capacity = 2048                    # knots per trajectory in the device workspace (status 3 if exceeded)
         self.last_batch = None                       # counters / collision flags of the latest batch
+        # Integrator failures (counters.status 1 = step cap / dt <= 0, 2 = non-finite state) are NOT collisions.  Policy
+        # (SURVEY.md 8b "Errors"): the trajectory scores 1e30 so that the optimiser moves on, the batch counts them in
+        # last_batch["n_failed"] (summed over ranks), a RuntimeWarning names the count -- and with
+        # raise_on_integration_failure = True every rank raises FloatingPointError instead, as compute_trajectory does.
+        self.raise_on_integration_failure = False
 
     # ------------------------------------------------------------------------------------------
     def get_bounds(self) -> Union[np.ndarray, np.ndarray]:
@@ -81,15 +91,47 @@ class udp_initial_condition:
         # the first event point found inside the mesh (same fitness vector, fewer gravity evaluations); the
         # compute_trajectory API keeps the reference behaviour and integrates to final_time
         p = params_from_args(args, stop_on_collision=1)
-        lo, hi = shard_bounds(len(xs))
-        local = ctx.population_fitness_host(p, xs[lo:hi], fixed, n_man, self.knot_capacity) if hi > lo else None
-        short = local is not None and bool((local["counters"]["status"] == 3).any())
-        # the flag travels with the fitness slices: every rank raises, none is left waiting in the collective
-        fit, short = gather_population_fitness(None if local is None else local["fitness"], len(xs), ctx,
-                                               local_flag=short, return_flag=True)
+        n = len(xs)
+        rank, w = P.world()
+        if w == 1:
+            local = ctx.population_fitness_host(p, xs, fixed, n_man, self.knot_capacity)
+            fit = local["fitness"]
+            status = local["counters"]["status"]
+            short, failed = int((status == 3).sum()), int(((status == 1) | (status == 2)).sum())
+        elif P._dist().get_backend() == "nccl":
+            # rows dealt by predicted cost, everything device-side between the H2D copy of the chromosomes and the
+            # D2H copy of the gathered fitness vector (parallel.py)
+            r = P.sharded_population_fitness(ctx, p, ctx.to_device_pinned(xs), fixed, n_man, self.knot_capacity)
+            out = ctx.torch.cat((r["fitness"], r["flags"])).cpu().numpy()
+            fit, short, failed = out[:n], int(out[n]), int(out[n + 1])
+            local = r["local"]
+            if local is not None:
+                local = {k: v.cpu().numpy() for k, v in local.items()}
+                local["counters"] = local["counters"].view(ctx_counters_dtype())
+                local["rows"] = r["order"].cpu().numpy()[rank::w]
+        else:
+            # any other backend (gloo): the same dealing with the collectives on host arrays
+            lo, hi = P.shard_bounds(n, rank, w)
+            cost = ctx.predict_cost(p, ctx._dev(xs[lo:hi]), fixed, n_man).cpu().numpy() if hi > lo else np.zeros(0, np.int32)
+            order = P.cost_order_host(P.gather_costs_host(cost, n))
+            rows = P.deal_host(order, rank, w)
+            local = ctx.population_fitness_host(p, xs[rows], fixed, n_man, self.knot_capacity) if len(rows) else None
+            fit, (short, failed) = P.exchange_dealt(None if local is None else local["fitness"],
+                                                    None if local is None else local["counters"]["status"], order, n)
+            if local is not None:
+                local["rows"] = rows
         self.last_batch = local
+        if local is not None:
+            local["n_failed"] = failed
         if short:
             raise RuntimeError("a trajectory needs more knots than udp.knot_capacity")
+        if failed:
+            msg = (f"{failed} of {len(xs)} trajectories failed to integrate (step cap or non-finite state); "
+                   "they score 1e30 like collisions -- see udp.last_batch['counters']['status']")
+            if self.raise_on_integration_failure:
+                raise FloatingPointError(msg)
+            import warnings
+            warnings.warn(msg, RuntimeWarning, stacklevel=3)
         return fit
 
     # pygmo deep-copies / pickles the UDP: nothing device-side lives on the object

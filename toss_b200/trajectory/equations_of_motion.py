@@ -9,7 +9,7 @@ from math import radians
 
 import numpy as np
 
-from .._runtime import any_context, context_for_args, params_from_args
+from .._runtime import bare_context, context_for_args, params_from_args
 
 
 def setup_spin_axis(args):
@@ -37,7 +37,7 @@ def compute_motion(t: float, x: np.ndarray, args) -> np.ndarray:
 
 def rotate_point(t: float, x: np.ndarray, spin_axis: np.ndarray, spin_velocity: float) -> np.ndarray:
     """Quaternion(axis=spin_axis, angle=-(spin_velocity*t)).rotate(x) (:98-117)."""
-    ctx = any_context()
+    ctx = bare_context()
     out = ctx.rotate_points(np.asarray(spin_axis, dtype=np.float64), float(spin_velocity), np.array([float(t)]),
                             np.asarray(x, dtype=np.float64).reshape(1, 3))
     return out.cpu().numpy()[0]

@@ -16,22 +16,20 @@ def get_trajectory_adaptive_step(list_of_ode_objects: list) -> Union[np.ndarray,
 
 def get_trajectory_fixed_step(args, list_of_ode_objects: list) -> Union[np.ndarray, np.ndarray]:
     """positions (3,N), velocities (3,N), timesteps (N) at the fixed measurement period (:28-76).
-    The sample -> segment bookkeeping is the reference's; the dense output of every segment is
-    evaluated on the GPU (TrajectorySegment._OdeSystem__sol -> toss_dense_eval)."""
-    timesteps = np.arange(args.problem.start_time, args.problem.final_time, args.problem.measurement_period)
-    positions = np.empty((3, len(timesteps)), dtype=np.float64)
-    velocities = np.empty((3, len(timesteps)), dtype=np.float64)
-    start_idx = 0
-    for ode_object in list_of_ode_objects:
-        ode_end_time = ode_object.t[-1]
-        end_time_idx = (np.abs(timesteps - ode_end_time)).argmin()
-        if ode_end_time < timesteps[end_time_idx]:
-            end_time_idx -= 1
-        if end_time_idx >= start_idx:
-            dense = np.transpose(ode_object._OdeSystem__sol(timesteps[start_idx:end_time_idx + 1]))
-            positions[:, start_idx:end_time_idx + 1] = dense[0:3, :]
-            velocities[:, start_idx:end_time_idx + 1] = dense[3:6, :]
-        start_idx = end_time_idx + 1
-        if len(timesteps) - 1 < start_idx:
-            break
-    return positions, velocities, timesteps
+
+    One device call: the knots of all segments go to the GPU as a one-trajectory workspace and `toss_resample`
+    (csrc/fitness.cu: resample_kernel) assigns every sample to its segment -- a sample at a manoeuvre time belongs
+    to the earlier segment, a segment may serve no sample -- and evaluates the cubic-Hermite
+    dense output there.  Samples past the last knot (which the reference leaves as np.empty garbage) come out as
+    the last segment's extrapolation."""
+    from .._runtime import context_for_args, params_from_args
+    segments = []
+    for seg in list_of_ode_objects:
+        if not hasattr(seg, "f"):
+            raise TypeError("get_trajectory_fixed_step needs the segment objects compute_trajectory returns "
+                            "(knot slopes .f are part of the dense output)")
+        segments.append((seg.t, seg.y, seg.f))
+    ctx = next((seg._ctx for seg in list_of_ode_objects if getattr(seg, "_ctx", None) is not None), None)
+    if ctx is None:
+        ctx = context_for_args(args)
+    return ctx.resample_segments(params_from_args(args), segments)
