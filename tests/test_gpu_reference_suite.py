@@ -131,8 +131,8 @@ def test_covered_space_perfect_ratio_and_random_sample():
     x, y, z = T.sphere2cart(R.ravel(), TH.ravel(), PH.ravel())
     pos = np.vstack((x, y, z))
     ts = np.arange(pos.shape[1], dtype=np.float64)
-    from toss_b200._runtime import any_context
-    rot = any_context().rotate_points(args.body.spin_axis, args.body.spin_velocity, -ts, pos.T.copy()).cpu().numpy().T
+    from toss_b200._runtime import bare_context
+    rot = bare_context().rotate_points(args.body.spin_axis, args.body.spin_velocity, -ts, pos.T.copy()).cpu().numpy().T
     cov = T.compute_space_coverage(1, args.body.spin_axis, args.body.spin_velocity, np.ascontiguousarray(rot),
                                    args.problem.fixed_velocity, ts, 2, 8, r, th, ph, bt)
     assert cov >= 1

@@ -30,11 +30,20 @@
 //   kPairRowSmem  the same, plus `scratch` = 96 doubles of shared memory owned by the warp: the out-of-range edge
 //                 terms of the row are compacted across the lanes (below).
 enum : int { kPairLane = 0, kPairRow = 1, kPairRowSmem = 2 };
-template <int kMode = kPairLane, class Fld>
-__device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz, double &SA, double &SB,
-                                       double &hpA_out, double &hpB_out, double *scratch = nullptr)
+
+// Everything of a pair term that does not depend on the tier: distances, plane / edge heights, the seven quotients
+// (ONE division), their squares and the high words the range tests look at.  (A caller that only needs some of the
+// fields leaves the rest to dead-code elimination.)
+struct PairFront {
+    double hpA, hpB, hA0, hA1, hA2, hB0, hB1, hB2;
+    double z0, z1, z2, z3, z4, z0s, z1s, z2s, z3s, z4s, qA, qB, qAs, qBs;
+    double a0, a1, a2, a3, a4, numA, numB, denA, denB, G0, G1, G2, G3, G4;
+    int hz0, hz1, hz2, hz3, hz4, hqA, hqB, hdA, hdB, hzmax, hqmax, hdmin;
+};
+template <class Fld>
+__device__ __forceinline__ PairFront pair_front(Fld fld, double Px, double Py, double Pz)
 {
-    constexpr bool kCompact = kMode == kPairRowSmem;
+    PairFront F;
     const double r0x = fld(0) - Px, r0y = fld(1) - Py, r0z = fld(2) - Pz;
     const double r1x = fld(3) - Px, r1y = fld(4) - Py, r1z = fld(5) - Pz;
     const double r2x = fld(6) - Px, r2y = fld(7) - Py, r2z = fld(8) - Pz;
@@ -43,39 +52,39 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
     const double l1 = tm_sqrt(fma(r1z, r1z, fma(r1y, r1y, r1x * r1x)));
     const double l2 = tm_sqrt(fma(r2z, r2z, fma(r2y, r2y, r2x * r2x)));
     const double l3 = tm_sqrt(fma(r3z, r3z, fma(r3y, r3y, r3x * r3x)));
-    const double hpA = fma(fld(14), r0z, fma(fld(13), r0y, fld(12) * r0x));     // N_A . r0
-    const double hpB = fma(fld(17), r1z, fma(fld(16), r1y, fld(15) * r1x));     // N_B . r1 (B's first vertex)
-    const double hA0 = fma(fld(20), r0z, fma(fld(19), r0y, fld(18) * r0x));     // A: e0 at v0, e1 at v1, e2 at v2
-    const double hA1 = fma(fld(23), r1z, fma(fld(22), r1y, fld(21) * r1x));
-    const double hA2 = fma(fld(26), r2z, fma(fld(25), r2y, fld(24) * r2x));
-    const double hB0 = fma(fld(29), r1z, fma(fld(28), r1y, fld(27) * r1x));     // B: e0 at v1, e3 at v0, e4 at v3
-    const double hB1 = fma(fld(32), r0z, fma(fld(31), r0y, fld(30) * r0x));
-    const double hB2 = fma(fld(35), r3z, fma(fld(34), r3y, fld(33) * r3x));
-    const double a0 = l0 + l1, a1 = l1 + l2, a2 = l2 + l0, a3 = l0 + l3, a4 = l3 + l1;
+    F.hpA = fma(fld(14), r0z, fma(fld(13), r0y, fld(12) * r0x));     // N_A . r0
+    F.hpB = fma(fld(17), r1z, fma(fld(16), r1y, fld(15) * r1x));     // N_B . r1 (B's first vertex)
+    F.hA0 = fma(fld(20), r0z, fma(fld(19), r0y, fld(18) * r0x));     // A: e0 at v0, e1 at v1, e2 at v2
+    F.hA1 = fma(fld(23), r1z, fma(fld(22), r1y, fld(21) * r1x));
+    F.hA2 = fma(fld(26), r2z, fma(fld(25), r2y, fld(24) * r2x));
+    F.hB0 = fma(fld(29), r1z, fma(fld(28), r1y, fld(27) * r1x));     // B: e0 at v1, e3 at v0, e4 at v3
+    F.hB1 = fma(fld(32), r0z, fma(fld(31), r0y, fld(30) * r0x));
+    F.hB2 = fma(fld(35), r3z, fma(fld(34), r3y, fld(33) * r3x));
+    F.a0 = l0 + l1, F.a1 = l1 + l2, F.a2 = l2 + l0, F.a3 = l0 + l3, F.a4 = l3 + l1;
     const double d01 = fma(r0z, r1z, fma(r0y, r1y, r0x * r1x));
     const double d12 = fma(r1z, r2z, fma(r1y, r2y, r1x * r2x));
     const double d20 = fma(r2z, r0z, fma(r2y, r0y, r2x * r0x));
     const double d03 = fma(r0z, r3z, fma(r0y, r3y, r0x * r3x));
     const double d31 = fma(r3z, r1z, fma(r3y, r1y, r3x * r1x));
     const double l01 = l0 * l1;
-    const double denA = fma(l2, d01, fma(l1, d20, fma(l0, d12, l01 * l2)));
-    const double denB = fma(l3, d01, fma(l0, d31, fma(l1, d03, l01 * l3)));
-    const double numA = hpA * fld(41), numB = hpB * fld(42);
-    const double G0 = fld(36), G1 = fld(37), G2 = fld(38), G3 = fld(39), G4 = fld(40);
+    F.denA = fma(l2, d01, fma(l1, d20, fma(l0, d12, l01 * l2)));
+    F.denB = fma(l3, d01, fma(l0, d31, fma(l1, d03, l01 * l3)));
+    F.numA = F.hpA * fld(41), F.numB = F.hpB * fld(42);
+    F.G0 = fld(36), F.G1 = fld(37), F.G2 = fld(38), F.G3 = fld(39), F.G4 = fld(40);
     // One division serves the five edge quotients and the two solid-angle quotients (X Y is a product of lengths and
     // of the two solid-angle denominators: it only has to be non-zero; were a denominator exactly 0 every quotient
     // would come out non-finite and every term would take its own way below).
-    const double P01 = a0 * a1, P2A = a2 * denA, P34 = a3 * a4;
-    const double X = P01 * P2A, Y = P34 * denB;
+    const double P01 = F.a0 * F.a1, P2A = F.a2 * F.denA, P34 = F.a3 * F.a4;
+    const double X = P01 * P2A, Y = P34 * F.denB;
     const double inv = tm_div(1.0, X * Y);
     const double iX = Y * inv, iY = X * inv;
-    const double i01 = P2A * iX, i2A = P01 * iX, i34 = denB * iY, iB = P34 * iY;
-    const double z0 = (G0 * a1) * i01, z1 = (G1 * a0) * i01, z2 = (G2 * denA) * i2A;
-    const double qA = (numA * a2) * i2A;
-    const double z3 = (G3 * a4) * i34, z4 = (G4 * a3) * i34;
-    const double qB = numB * iB;
-    const double z0s = z0 * z0, z1s = z1 * z1, z2s = z2 * z2, z3s = z3 * z3, z4s = z4 * z4;
-    const double qAs = qA * qA, qBs = qB * qB;
+    const double i01 = P2A * iX, i2A = P01 * iX, i34 = F.denB * iY, iB = P34 * iY;
+    F.z0 = (F.G0 * F.a1) * i01, F.z1 = (F.G1 * F.a0) * i01, F.z2 = (F.G2 * F.denA) * i2A;
+    F.qA = (F.numA * F.a2) * i2A;
+    F.z3 = (F.G3 * F.a4) * i34, F.z4 = (F.G4 * F.a3) * i34;
+    F.qB = F.numB * iB;
+    F.z0s = F.z0 * F.z0, F.z1s = F.z1 * F.z1, F.z2s = F.z2 * F.z2, F.z3s = F.z3 * F.z3, F.z4s = F.z4 * F.z4;
+    F.qAs = F.qA * F.qA, F.qBs = F.qB * F.qB;
     // Range tests.  An edge seen under a large angle (z^2 >= kZ2Max) takes a division of its own and the ln-based
     // atanh; a face seen under a large solid angle or from behind (den <= 0 or q^2 >= kQ2Max) the full-range atan2.
     // Each term chooses for itself; the rule is part of the arithmetic specification.  The
@@ -83,43 +92,57 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
     // alone (a NaN pattern is above every finite one): the whole test costs two 3-input integer maxima, one
     // max, one min and three compares on the integer pipe instead of nine FP64-pipe compares -- the FP64 pipe (two
     // issue slots per instruction) is what bounds this loop.
-    const int hz0 = __double2hiint(z0s), hz1 = __double2hiint(z1s), hz2 = __double2hiint(z2s),
-              hz3 = __double2hiint(z3s), hz4 = __double2hiint(z4s);
-    const int hqA = __double2hiint(qAs), hqB = __double2hiint(qBs), hdA = __double2hiint(denA),
-              hdB = __double2hiint(denB);
-    const int hzmax = max(max(max(hz0, hz1), hz2), max(hz3, hz4)), hqmax = max(hqA, hqB), hdmin = min(hdA, hdB);
+    F.hz0 = __double2hiint(F.z0s), F.hz1 = __double2hiint(F.z1s), F.hz2 = __double2hiint(F.z2s),
+    F.hz3 = __double2hiint(F.z3s), F.hz4 = __double2hiint(F.z4s);
+    F.hqA = __double2hiint(F.qAs), F.hqB = __double2hiint(F.qBs), F.hdA = __double2hiint(F.denA),
+    F.hdB = __double2hiint(F.denB);
+    F.hzmax = max(max(max(F.hz0, F.hz1), F.hz2), max(F.hz3, F.hz4)), F.hqmax = max(F.hqA, F.hqB),
+    F.hdmin = min(F.hdA, F.hdB);
+    return F;
+}
+
+// FAR ROW: every z^2 and q^2 of the 32 pairs below 0x3F647AE1'00000000 (= 0.0025 - 5e-10) and every face seen
+// from the front -- 84 % (init-like) to 97 % (converged-like) of the rows a population evaluates.  The row
+// takes 4-coefficient polynomials (17 FP64 instructions less per pair); the tier is a property of (row, field
+// point), so it does not depend on which warp evaluates the row.  Half values, as in the general tail.
+__device__ __forceinline__ bool pair_lane_far(const PairFront &F) { return (max(F.hzmax, F.hqmax) < kHiFar) & (F.hdmin > 0); }
+__device__ __forceinline__ void pair_tail_far(const PairFront &F, double &SA, double &SB)
+{
+    const double f0 = tm_atanh_far(F.z0, F.z0s), f1 = tm_atanh_far(F.z1, F.z1s), f2 = tm_atanh_far(F.z2, F.z2s),
+                 f3 = tm_atanh_far(F.z3, F.z3s), f4 = tm_atanh_far(F.z4, F.z4s);
+    const double wA = tm_atan_far(F.qA, F.qAs), wB = tm_atan_far(F.qB, F.qBs);
+    SA = fma(-F.hpA, wA, fma(F.hA2, f2, fma(F.hA1, f1, F.hA0 * f0)));
+    SB = fma(-F.hpB, wB, fma(F.hB2, f4, fma(F.hB1, f3, F.hB0 * f0)));
+}
+// MIDDLE ROW: every z^2 and q^2 below 0x3F847AE1'00000000 (= 0.01 - 2e-9), faces from the front -- another
+// 12 % of the rows of an init-like population (whose trajectories start 5 km above the surface: hardly any
+// of them is far all the time, and a tile ring advances at the pace of its slowest warp): 5-coefficient
+// atanh, the 5-coefficient atan, no range tests.
+__device__ __forceinline__ bool pair_lane_mid(const PairFront &F) { return (max(F.hzmax, F.hqmax) < kHiQ2Max) & (F.hdmin > 0); }
+__device__ __forceinline__ void pair_tail_mid(const PairFront &F, double &SA, double &SB)
+{
+    const double f0 = tm_atanh_mid(F.z0, F.z0s), f1 = tm_atanh_mid(F.z1, F.z1s), f2 = tm_atanh_mid(F.z2, F.z2s),
+                 f3 = tm_atanh_mid(F.z3, F.z3s), f4 = tm_atanh_mid(F.z4, F.z4s);
+    const double wA = tm_atan_mm(F.qA, F.qAs), wB = tm_atan_mm(F.qB, F.qBs);
+    SA = fma(-F.hpA, wA, fma(F.hA2, f2, fma(F.hA1, f1, F.hA0 * f0)));
+    SB = fma(-F.hpB, wB, fma(F.hB2, f4, fma(F.hB1, f3, F.hB0 * f0)));
+}
+
+// the rows that are left (and every pair of the thread-per-point kernel): each term chooses its own path
+template <int kMode>
+__device__ __forceinline__ void pair_tail_general(const PairFront &F, double &SA, double &SB, double *scratch)
+{
+    constexpr bool kCompact = kMode == kPairRowSmem;
     constexpr unsigned kFull = 0xffffffffu;
-    hpA_out = hpA;
-    hpB_out = hpB;
-    if (kMode != kPairLane) {
-        // FAR ROW: every z^2 and q^2 of the 32 pairs below 0x3F647AE1'00000000 (= 0.0025 - 5e-10) and every face seen
-        // from the front -- 84 % (init-like) to 97 % (converged-like) of the rows a population evaluates.  The row
-        // takes 4-coefficient polynomials (17 FP64 instructions less per pair); the tier is a property of (row, field
-        // point), so it does not depend on which warp evaluates the row.  Half values, as below.
-        const bool lane_far = (max(hzmax, hqmax) < kHiFar) & (hdmin > 0);
-        if (__all_sync(kFull, lane_far)) {
-            const double f0 = tm_atanh_far(z0, z0s), f1 = tm_atanh_far(z1, z1s), f2 = tm_atanh_far(z2, z2s),
-                         f3 = tm_atanh_far(z3, z3s), f4 = tm_atanh_far(z4, z4s);
-            const double wA = tm_atan_far(qA, qAs), wB = tm_atan_far(qB, qBs);
-            SA = fma(-hpA, wA, fma(hA2, f2, fma(hA1, f1, hA0 * f0)));
-            SB = fma(-hpB, wB, fma(hB2, f4, fma(hB1, f3, hB0 * f0)));
-            return;
-        }
-        // MIDDLE ROW: every z^2 and q^2 below 0x3F847AE1'00000000 (= 0.01 - 2e-9), faces from the front -- another
-        // 12 % of the rows of an init-like population (whose trajectories start 5 km above the surface: hardly any
-        // of them is far all the time, and a tile ring advances at the pace of its slowest warp): 5-coefficient
-        // atanh, the 5-coefficient atan, no range tests.
-        const bool lane_mid = (max(hzmax, hqmax) < kHiQ2Max) & (hdmin > 0);
-        if (__all_sync(kFull, lane_mid)) {
-            const double f0 = tm_atanh_mid(z0, z0s), f1 = tm_atanh_mid(z1, z1s), f2 = tm_atanh_mid(z2, z2s),
-                         f3 = tm_atanh_mid(z3, z3s), f4 = tm_atanh_mid(z4, z4s);
-            const double wA = tm_atan_mm(qA, qAs), wB = tm_atan_mm(qB, qBs);
-            SA = fma(-hpA, wA, fma(hA2, f2, fma(hA1, f1, hA0 * f0)));
-            SB = fma(-hpB, wB, fma(hB2, f4, fma(hB1, f3, hB0 * f0)));
-            return;
-        }
-    }
-    // the rows that are left: the lane-per-pair kernels take an 11-coefficient atanh up to z^2 < 0.16 (a third as many
+    const double z0 = F.z0, z1 = F.z1, z2 = F.z2, z3 = F.z3, z4 = F.z4;
+    const double z0s = F.z0s, z1s = F.z1s, z2s = F.z2s, z3s = F.z3s, z4s = F.z4s;
+    const double qA = F.qA, qB = F.qB, qAs = F.qAs, qBs = F.qBs;
+    const double G0 = F.G0, G1 = F.G1, G2 = F.G2, G3 = F.G3, G4 = F.G4;
+    const double a0 = F.a0, a1 = F.a1, a2 = F.a2, a3 = F.a3, a4 = F.a4;
+    const double numA = F.numA, numB = F.numB, denA = F.denA, denB = F.denB;
+    const int hz0 = F.hz0, hz1 = F.hz1, hz2 = F.hz2, hz3 = F.hz3, hz4 = F.hz4, hqA = F.hqA, hqB = F.hqB, hdA = F.hdA,
+              hdB = F.hdB, hzmax = F.hzmax, hqmax = F.hqmax, hdmin = F.hdmin;
+    // the lane-per-pair kernels take an 11-coefficient atanh up to z^2 < 0.16 (a third as many
     // rows with out-of-range edge terms as with the 7-coefficient one up to 0.04; the extra 20 FP64 instructions fall
     // on the 5 % of the rows that get here); the thread-per-point kernel keeps 7 coefficients up to 0.04
     constexpr int kZ2Max = kMode == kPairLane ? kHiZ2Max : kHiZ2Wide;
@@ -195,8 +218,29 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
         if (isA) omA = v;
         else omB = v;
     }
-    SA = fma(-hpA, omA, fma(hA2, ln2, fma(hA1, ln1, hA0 * ln0)));
-    SB = fma(-hpB, omB, fma(hB2, ln4, fma(hB1, ln3, hB0 * ln0)));
+    SA = fma(-F.hpA, omA, fma(F.hA2, ln2, fma(F.hA1, ln1, F.hA0 * ln0)));
+    SB = fma(-F.hpB, omB, fma(F.hB2, ln4, fma(F.hB1, ln3, F.hB0 * ln0)));
+}
+
+template <int kMode = kPairLane, class Fld>
+__device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz, double &SA, double &SB,
+                                       double &hpA_out, double &hpB_out, double *scratch = nullptr)
+{
+    constexpr unsigned kFull = 0xffffffffu;
+    const PairFront F = pair_front(fld, Px, Py, Pz);
+    hpA_out = F.hpA;
+    hpB_out = F.hpB;
+    if (kMode != kPairLane) {
+        if (__all_sync(kFull, pair_lane_far(F))) {
+            pair_tail_far(F, SA, SB);
+            return;
+        }
+        if (__all_sync(kFull, pair_lane_mid(F))) {
+            pair_tail_mid(F, SA, SB);
+            return;
+        }
+    }
+    pair_tail_general<kMode>(F, SA, SB, scratch);
 }
 
 // acc += (N_A S_A + N_B S_B) / 2 (and pot += (hp_A S_A + hp_B S_B) / 2): pair_S works in exact halves

@@ -298,8 +298,9 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 // compute_trajectory.py:75-121: int32 truncation, stable sort, equal times merged (dv summed)
                 if (lane == 0) {
                     const int M = a.n_man;
-                    int idx[64];
-                    int32_t tm[64];
+                    // sort scratch in the warp's shared-memory scratch (free between sweeps): no local-memory arrays
+                    int *idx = reinterpret_cast<int *>(scr);
+                    int32_t *tm = reinterpret_cast<int32_t *>(scr) + 64;
                     for (int k = 0; k < M; ++k) {
                         tm[k] = (int32_t)X(7 + 5 * k);
                         idx[k] = k;
@@ -332,8 +333,10 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                         }
                     }
                     seg_t[n + 1] = (double)(int32_t)p.final_time;
-                    a.n_seg[traj] = n + 1;
-                    for (int s = 0; s <= n + 1; ++s) a.intervals[(size_t)traj * (a.n_man + 2) + s] = seg_t[s];
+                    if (!kProxy) {   // (the proxy run has no workspace)
+                        a.n_seg[traj] = n + 1;
+                        for (int s = 0; s <= n + 1; ++s) a.intervals[(size_t)traj * (a.n_man + 2) + s] = seg_t[s];
+                    }
                     meta[0] = (double)(n + 1);   // segment count travels to the other lanes through shared memory
                 }
                 __syncwarp();
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                 status = 0;
                 n_acc = n_rej = n_ev = collided = stopped = ray_sweep = 0;
                 n_rhs = 0;
-                if (lane == 0) a.seg_start[(size_t)traj * (a.n_man + 2)] = 0;
+                if (!kProxy && lane == 0) a.seg_start[(size_t)traj * (a.n_man + 2)] = 0;
             }
         }
         if (!active) {
@@ -622,7 +625,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     // compute_trajectory.py:134-136: velocity REPLACED by the manoeuvre's dv
                     if (lane >= 3 && lane < 6) sy[lane] = sdv[3 * (seg - 1) + (lane - 3)];
                     __syncwarp();
-                    if (lane == 0) a.seg_start[(size_t)traj * (a.n_man + 2) + seg] = nk;
+                    if (!kProxy && lane == 0) a.seg_start[(size_t)traj * (a.n_man + 2) + seg] = nk;
                     t = seg_t[seg];
                     tf = seg_t[seg + 1];
                     dt = p.initial_time_step;
