@@ -84,6 +84,7 @@ def lib():
         L.orc_mesh_pairs.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         L.orc_gravity.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p, C.c_int]
         L.orc_gravity_direct.argtypes = [C.c_void_p, c_double_p, C.c_int64, c_double_p, c_double_p]
+        L.orc_gravity_tiers.argtypes = [C.c_void_p, c_double_p, C.c_int64, C.POINTER(C.c_int64)]
         L.orc_math_probe.argtypes = [C.c_int, c_double_p, c_double_p, C.c_int64, c_double_p, c_double_p]
         L.orc_rotate_point.argtypes = [C.c_double, c_double_p, c_double_p, C.c_double, c_double_p]
         L.orc_compute_motion.argtypes = [C.c_void_p, C.POINTER(OrcParams), C.c_double, c_double_p, c_double_p]
@@ -229,6 +230,14 @@ def gravity_direct(mesh: Mesh, pts):
     acc = np.empty_like(pts)
     lib().orc_gravity_direct(mesh.handle, _dp(pts), len(pts), _dp(acc), None)
     return acc
+
+
+def gravity_tiers(mesh: Mesh, pts):
+    """Census of the paths `gravity` takes for these points: dict(far_rows, mid_rows, term_rows, ln_terms, atan2_terms)."""
+    pts = _f64(pts).reshape(-1, 3)
+    out = (C.c_int64 * 5)()
+    lib().orc_gravity_tiers(mesh.handle, _dp(pts), len(pts), out)
+    return dict(zip(("far_rows", "mid_rows", "term_rows", "ln_terms", "atan2_terms"), [int(x) for x in out]))
 
 
 MATH_FN = dict(two_atanh=0, log=1, atan2=2, sincos=3, root8=4, root4=5, atan_series8=6, div=7, sqrt=8,

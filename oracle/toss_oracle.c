@@ -494,6 +494,33 @@ static void gravity_point(const orc_mesh *m, const double P[3], double acc[3], d
     if (pot) *pot = 0.5 * m->Grho * orc_butterfly32(sv);
 }
 
+/* Census of the paths gravity_point takes for the given points (tests: every tier must have been exercised):
+ * out[0] far rows, out[1] middle rows, out[2] rows where every term chooses for itself, out[3] edge terms that took
+ * the ln-based atanh, out[4] solid-angle terms that took the full-range atan2. */
+void orc_gravity_tiers(const orc_mesh *m, const double *pts, int64_t n, int64_t out[5])
+{
+    pair_pre pre[32];
+    for (int k = 0; k < 5; ++k) out[k] = 0;
+    for (int64_t ip = 0; ip < n; ++ip) {
+        for (int base = 0; base < m->n_pairs; base += 32) {
+            const int cnt = m->n_pairs - base < 32 ? m->n_pairs - base : 32;
+            int row_tier = 2;
+            for (int i = 0; i < cnt; ++i) {
+                pair_prelim(m->prec + (size_t)(base + i) * PREC, pts + 3 * ip, &pre[i]);
+                const int t = pair_tier(&pre[i]);
+                if (t < row_tier) row_tier = t;
+            }
+            out[2 - row_tier] += 1;
+            if (row_tier == 0)
+                for (int i = 0; i < cnt; ++i) {
+                    for (int k = 0; k < 5; ++k) out[3] += !(orc_hi(pre[i].zs[k]) < ORC_HI_Z2MAX);
+                    for (int f = 0; f < 2; ++f)
+                        out[4] += !((orc_hi(pre[i].den[f]) > 0) && (orc_hi(pre[i].qs[f]) < ORC_HI_Q2MAX));
+                }
+        }
+    }
+}
+
 void orc_gravity_direct(const orc_mesh *m, const double *pts, int64_t n, double *acc, double *pot)
 {
     for (int64_t i = 0; i < n; ++i) gravity_point_direct(m, pts + 3 * i, acc + 3 * i, pot ? pot + i : NULL);

@@ -75,6 +75,9 @@ void orc_gravity(const orc_mesh *m, const double *pts, int64_t n, double *acc, d
 /* the same sum with LN/AN transcribed literally from Tsoulis (2012); ~1e-12 relative rounding
  * noise on the fine meshes (tests/test_oracle_gravity.py) -- cross-check only. */
 void orc_gravity_direct(const orc_mesh *m, const double *pts, int64_t n, double *acc, double *pot);
+/* census of the tiers / fall-backs orc_gravity takes for these points: far rows, middle rows, per-term rows,
+ * ln-based edge terms, full-range atan2 terms */
+void orc_gravity_tiers(const orc_mesh *m, const double *pts, int64_t n, int64_t out[5]);
 
 /* equations_of_motion.py:98-117 */
 void orc_rotate_point(double t, const double x[3], const double axis[3], double w, double out[3]);

@@ -167,3 +167,24 @@ def test_compute_motion_quirks():
     rot = O.rotate_point(t, y[:3], np.array(p.spin_axis[:]), p.spin_velocity)
     assert np.array_equal(out[:3], y[3:])
     assert np.allclose(out[3:], -O.gravity(m, rot)[0], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("name", ["lp", "full"])
+def test_gravity_vs_committed_mpmath_truth(name):
+    """The meshes the benchmark runs on, at the north-star tolerance: 44 field points each (shell, 1-3.5 km above the
+    surface, 3..600 m above faces and vertices, inside the body) against tests/golden/gravity_truth_<mesh>.npz --
+    50-digit mpmath, literal Tsoulis formula, written by tools/gen_gravity_truth.py with nothing shared with the
+    oracle.  Every tier and every fall-back of the production arithmetic must have been taken."""
+    from pathlib import Path
+    d = np.load(Path(__file__).parent / "golden" / f"gravity_truth_{name}.npz")
+    v, f = O.load_mesh(name)
+    m = O.Mesh(v, f)
+    acc = O.gravity(m, d["points"])
+    rel = np.linalg.norm(acc - d["acc"], axis=1) / np.linalg.norm(d["acc"], axis=1)
+    assert rel.max() < 5e-14, rel.max()
+    census = O.gravity_tiers(m, d["points"])
+    assert min(census.values()) > 0, census           # far, middle, per-term rows; ln-based atanh; full-range atan2
+    # the literal double-precision transcription cannot serve as the 1e-12 anchor on these meshes
+    lit = O.gravity_direct(m, d["points"])
+    rel_lit = np.linalg.norm(lit - d["acc"], axis=1) / np.linalg.norm(d["acc"], axis=1)
+    assert rel_lit.max() < 2e-11 and rel_lit.max() > 20 * rel.max()
