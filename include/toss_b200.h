@@ -211,6 +211,17 @@ int toss_pack_result(toss_ctx *ctx, const double *d_fitness_local, const toss_co
 int toss_unpack_result(toss_ctx *ctx, const double *d_recv, const int32_t *d_order, int n, int world, int cap,
                        double *d_fitness, double *d_flags, uintptr_t stream);
 
+/* ---- the optimiser's candidates, generated where they are consumed ----------------------------
+ * Replaces the sampling step of pygmo's gaco (pg.gaco(...).evolve, toss.py:51-66 with default_cfg.toml:72-82): ants
+ * first_ant .. first_ant + n - 1 of generation `generation` draw a kernel k from the cumulative rank weights
+ * h_cum_weights[ker] and every gene h from N(h_archive_x[k][h], h_sigma[h]), re-drawn while outside
+ * [h_lb[h], h_ub[h]] (clamped after 64 draws), into d_x_out[n][dim] -- the chromosome matrix toss_population_fitness
+ * reads, so a generation's decision vectors never cross PCIe.  Counter-based random numbers: ant j's genes depend on
+ * (seed, generation, j) only (toss_b200/optimization/gaco.py has the numpy mirror). */
+int toss_gaco_sample(toss_ctx *ctx, const double *h_archive_x, int ker, int dim, const double *h_cum_weights,
+                     const double *h_sigma, const double *h_lb, const double *h_ub, uint64_t seed, uint64_t generation,
+                     int first_ant, int n, double *d_x_out, uintptr_t stream);
+
 /* Measures the FP64 FMA peak of the device (register-resident DFMA chains on every SM) in TFLOP/s;
  * the roofline denominator of bench.py (MEASURED_PEAKS.json has no FP64 entry). */
 int toss_measure_fp64_peak(toss_ctx *ctx, double *tflops_out);

@@ -60,7 +60,7 @@ EXPORTS = [
     "toss_fitness_eval", "toss_update_tensor", "toss_is_outside", "toss_population_fitness",
     "toss_population_fitness_host", "toss_measure_fp64_peak", "toss_launch_count", "toss_math_probe",
     "toss_selftest_div_sqrt", "toss_set_queue_order", "toss_predict_cost", "toss_cost_order", "toss_deal_rows",
-    "toss_pack_result", "toss_unpack_result",
+    "toss_pack_result", "toss_unpack_result", "toss_gaco_sample",
 ]
 
 _lib = None
@@ -125,6 +125,8 @@ def lib():
     L.toss_deal_rows.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, up]
     L.toss_pack_result.argtypes = [vp, vp, vp, i32, i32, vp, up]
     L.toss_unpack_result.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, up]
+    L.toss_gaco_sample.argtypes = [vp, c_double_p, i32, i32, c_double_p, c_double_p, c_double_p, c_double_p,
+                                   C.c_uint64, C.c_uint64, i32, i32, vp, up]
     L.toss_measure_fp64_peak.argtypes = [vp, c_double_p]
     L.toss_launch_count.restype = i64
     L.toss_launch_count.argtypes = [vp]
@@ -505,6 +507,20 @@ class Context:
         _check(lib().toss_unpack_result(self.h, recv.data_ptr(), order.data_ptr(), n, world, cap, fit.data_ptr(),
                                         flags.data_ptr(), self._stream()))
         return fit, flags
+
+    def gaco_sample(self, archive_x, cum_weights, sigma, lb, ub, seed: int, generation: int, first_ant: int, n: int,
+                    out=None):
+        """n candidates of generation `generation` (ants first_ant ..) drawn on the device into a CUDA (n, dim) tensor"""
+        t = self.torch
+        archive_x = _f64(archive_x)
+        ker, dim = archive_x.shape
+        cum, sigma, lb, ub = _f64(cum_weights), _f64(sigma), _f64(lb), _f64(ub)
+        if out is None:
+            out = t.empty((n, dim), dtype=t.float64, device=self.device)
+        _check(lib().toss_gaco_sample(self.h, _dp(archive_x), ker, dim, _dp(cum), _dp(sigma), _dp(lb), _dp(ub),
+                                      seed & 0xFFFFFFFFFFFFFFFF, generation, first_ant, n, out.data_ptr(),
+                                      self._stream()))
+        return out
 
     def math_probe(self, fn: int, a, b=None):
         """tmath.cuh function `fn` over arrays (tests): numpy out, or (sin, cos) for fn 3"""

@@ -65,6 +65,7 @@ int toss_ctx_destroy(toss_ctx *ctx)
     cudaFree(ctx->d_scratch);
     cudaFree(ctx->d_tensor_scratch);
     cudaFree(ctx->queue_scratch);
+    cudaFree(ctx->d_gaco_tab);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     delete ctx;
     return 0;
@@ -507,6 +508,16 @@ int toss_unpack_result(toss_ctx *ctx, const double *d_recv, const int32_t *d_ord
     TOSS_REQUIRE(ctx != nullptr, "toss_unpack_result: NULL context");
     TOSS_ENTER(ctx);
     return launch_unpack_result(ctx, d_recv, d_order, n, world, cap, d_fitness, d_flags, (cudaStream_t)stream);
+}
+
+int toss_gaco_sample(toss_ctx *ctx, const double *h_archive_x, int ker, int dim, const double *h_cum_weights,
+                     const double *h_sigma, const double *h_lb, const double *h_ub, uint64_t seed, uint64_t generation,
+                     int first_ant, int n, double *d_x_out, uintptr_t stream)
+{
+    TOSS_REQUIRE(ctx != nullptr, "toss_gaco_sample: NULL context");
+    TOSS_ENTER(ctx);
+    return launch_gaco_sample(ctx, h_archive_x, ker, dim, h_cum_weights, h_sigma, h_lb, h_ub, seed, generation, first_ant,
+                              n, d_x_out, (cudaStream_t)stream);
 }
 
 int toss_math_probe(toss_ctx *ctx, int fn, const double *d_a, const double *d_b, int64_t n, double *d_out,

@@ -88,6 +88,8 @@ struct toss_ctx {
     int64_t launches = 0;
     int queue_order_mode = 0;        // 0: the launcher orders the work queue itself (proxy run); 1: rows are pre-ordered
     int32_t *queue_scratch = nullptr;   // 256 B: work-queue cursor of toss_predict_cost's proxy run
+    double *d_gaco_tab = nullptr;       // toss_gaco_sample: archive | cumulative weights | sigma | lb | ub
+    size_t gaco_tab_words = 0;
 };
 
 void toss_set_error(const std::string &msg);
@@ -212,6 +214,9 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
 int launch_predict_cost(toss_ctx *ctx, const toss_params *p, const double *d_x, int pop, int dim, const double *h_fixed,
                         int n_fixed, int n_man, int32_t *d_cost, cudaStream_t st);
 int launch_cost_order(toss_ctx *ctx, const int32_t *d_cost, int n, int32_t *d_order, cudaStream_t st);
+int launch_gaco_sample(toss_ctx *ctx, const double *h_archive_x, int ker, int dim, const double *h_cum,
+                       const double *h_sigma, const double *h_lb, const double *h_ub, uint64_t seed, uint64_t generation,
+                       int first_ant, int n, double *d_x_out, cudaStream_t st);
 int launch_deal_rows(toss_ctx *ctx, const double *d_x, int n, int dim, const int32_t *d_order, int rank, int world,
                      double *d_x_local, cudaStream_t st);
 int launch_pack_result(toss_ctx *ctx, const double *d_fit, const toss_counters *d_cnt, int n_local, int cap,

@@ -4,7 +4,8 @@ Spacecraft are optimised one after the other; after each one the champion's traj
 voxels are OR-ed into args.problem.bool_tensor, which changes the coverage term of the next spacecraft
 (toss.py:104-145).  Where the reference spreads `udp.fitness` over a `pg.mp_bfe` process pool, every generation
 here is one `udp.batch_fitness` call.  With pygmo installed the optimiser is pygmo's GACO driven through
-`pg.bfe(pg.member_bfe())`; without it the built-in `GacoLite` restatement is used.
+`pg.bfe(pg.member_bfe())`; without it `toss_b200.optimization.gaco.Gaco`, which honours the same eleven parameters and
+draws every generation's candidates on the device (csrc/gaco.cu), is used.
 """
 from __future__ import annotations
 
@@ -13,7 +14,7 @@ import time
 import numpy as np
 
 from .fitness.fitness_function_utils import update_spherical_tensor_grid
-from .optimization.gaco_lite import GacoLite
+from .optimization.gaco import Gaco
 from .optimization.setup_parameters import setup_parameters
 from .optimization.setup_state import setup_initial_state_domain
 from .optimization.udp_initial_condition import udp_initial_condition
@@ -43,7 +44,7 @@ def load_uda(args, bfe=None, seed: int = 0):
         uda = pg.gaco(*params)
         uda.set_bfe(bfe)
         return pg.algorithm(uda)
-    return GacoLite(*params, seed=seed)
+    return Gaco(*params, seed=seed)
 
 
 def run_optimization(args, initial_state, lower_bounds, upper_bounds, seed: int = 0):

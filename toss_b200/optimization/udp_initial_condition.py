@@ -78,9 +78,22 @@ class udp_initial_condition:
             dvs = dvs.reshape(-1, dim)
         return self._evaluate(dvs)
 
+    def device_context(self):
+        """The device context this UDP evaluates on (mesh + voxel grid of self.args uploaded)."""
+        return context_for_args(self.args, need_grid=True)
+
+    def batch_fitness_device(self, d_xs) -> np.ndarray:
+        """`batch_fitness` for decision vectors that already live on the GPU: d_xs is a CUDA float64 tensor (n, dim),
+        e.g. the candidates `toss_gaco_sample` drew (optimization/gaco.py).  Returns the host fitness vector (n)."""
+        if d_xs.dim() != 2 or d_xs.shape[1] != len(self.lower_bounds):
+            raise ValueError(f"batch_fitness_device: expected (n, {len(self.lower_bounds)}), got {tuple(d_xs.shape)}")
+        return self._evaluate(d_xs)
+
     # ------------------------------------------------------------------------------------------
-    def _evaluate(self, xs: np.ndarray) -> np.ndarray:
+    def _evaluate(self, xs) -> np.ndarray:
+        """xs: host array (n, dim) or CUDA tensor (n, dim)"""
         args = self.args
+        on_device = not isinstance(xs, np.ndarray)
         n_man = int(args.problem.number_of_maneuvers)
         fixed = np.asarray(self.initial_condition, dtype=np.float64).reshape(-1)
         if fixed.size + xs.shape[1] != 7 + 5 * n_man:
@@ -93,7 +106,14 @@ class udp_initial_condition:
         p = params_from_args(args, stop_on_collision=1)
         n = len(xs)
         rank, w = P.world()
-        if w == 1:
+        if w == 1 and on_device:
+            r = ctx.population_fitness(p, xs, fixed, n_man, self.knot_capacity)
+            local = {k: v.cpu().numpy() for k, v in r.items()}
+            local["counters"] = local["counters"].view(ctx_counters_dtype())
+            fit = local["fitness"]
+            status = local["counters"]["status"]
+            short, failed = int((status == 3).sum()), int(((status == 1) | (status == 2)).sum())
+        elif w == 1:
             local = ctx.population_fitness_host(p, xs, fixed, n_man, self.knot_capacity)
             fit = local["fitness"]
             status = local["counters"]["status"]
@@ -101,7 +121,8 @@ class udp_initial_condition:
         elif P._dist().get_backend() == "nccl":
             # rows dealt by predicted cost, everything device-side between the H2D copy of the chromosomes and the
             # D2H copy of the gathered fitness vector (parallel.py)
-            r = P.sharded_population_fitness(ctx, p, ctx.to_device_pinned(xs), fixed, n_man, self.knot_capacity)
+            r = P.sharded_population_fitness(ctx, p, xs if on_device else ctx.to_device_pinned(xs), fixed, n_man,
+                                             self.knot_capacity)
             out = ctx.torch.cat((r["fitness"], r["flags"])).cpu().numpy()
             fit, short, failed = out[:n], int(out[n]), int(out[n + 1])
             local = r["local"]
@@ -111,6 +132,8 @@ class udp_initial_condition:
                 local["rows"] = r["order"].cpu().numpy()[rank::w]
         else:
             # any other backend (gloo): the same dealing with the collectives on host arrays
+            if on_device:
+                xs = xs.cpu().numpy()
             lo, hi = P.shard_bounds(n, rank, w)
             cost = ctx.predict_cost(p, ctx._dev(xs[lo:hi]), fixed, n_man).cpu().numpy() if hi > lo else np.zeros(0, np.int32)
             order = P.cost_order_host(P.gather_costs_host(cost, n))
