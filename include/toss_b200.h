@@ -86,8 +86,11 @@ int toss_ctx_destroy(toss_ctx *ctx);
  * (toss/optimization/setup_parameters.py:63) and the vertices/faces the ray caster reads
  * (toss/mesh/mesh_utility.py:70-89).  HOST arrays: verts V x 3 (metres), faces F x 3 (CCW outward).
  * Matches the faces into pairs that share an edge (the unit of the gravity sum: 4 vertex distances and 5 edge
- * terms per pair instead of 6 and 6) and precomputes the per-pair constants (normals, edge normals, edge
- * lengths, 2*area) -- what GravityEvaluable precomputes at construction (setup_parameters.py:63). */
+ * terms per pair instead of 6 and 6; host, integer work) and precomputes the per-pair constants (normals, edge
+ * normals, edge lengths, 2*area) in a kernel -- what GravityEvaluable precomputes at construction
+ * (setup_parameters.py:63).  Fails (error 2, toss_last_error says why) for a surface that is not closed and
+ * consistently oriented (an edge not shared by exactly two faces in opposite directions), for inward-pointing
+ * winding (negative volume) and for zero-area faces. */
 int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t *h_faces, int F, double density);
 int toss_mesh_num_faces(const toss_ctx *ctx);
 /* The pairing: n = toss_mesh_num_pairs records (fA, qA, fB) ascending in fA; A's edge slot qA (v_qA -> v_qA+1)
@@ -97,6 +100,11 @@ int toss_mesh_num_faces(const toss_ctx *ctx);
 int toss_mesh_num_pairs(const toss_ctx *ctx);
 int toss_mesh_pairs(const toss_ctx *ctx, int32_t *out);
 int toss_pair_faces(const int32_t *h_faces, int F, int V, int32_t *out);
+/* The per-pair constants as the device built them (pairs.cu: pair_tables_kernel): out = double[n_pairs][44], the
+ * 43 fields of a pair record (v0 v1 v2 v3 | N_A N_B | 3 + 3 in-plane edge normals | 5 edge lengths | 2A_A 2A_B) + one
+ * pad word.  For inspection and tests: the constants are plain IEEE + - * / sqrt in a fixed order, so a host
+ * re-computation reproduces them bit for bit. */
+int toss_mesh_pair_records(toss_ctx *ctx, double *h_out);
 
 /* Replaces args.problem.tensor_grid_r/theta/phi + bool_tensor
  * (toss/fitness/fitness_function_utils.py:231-279).  HOST arrays; bool_tensor is nr*nth*nph bytes. */

@@ -55,7 +55,7 @@ COUNTERS_DTYPE = np.dtype(
 
 EXPORTS = [
     "toss_version", "toss_last_error", "toss_ctx_create", "toss_ctx_destroy", "toss_mesh_upload",
-    "toss_mesh_num_faces", "toss_mesh_num_pairs", "toss_mesh_pairs", "toss_pair_faces", "toss_grid_upload", "toss_gravity_eval", "toss_compute_motion",
+    "toss_mesh_num_faces", "toss_mesh_num_pairs", "toss_mesh_pairs", "toss_mesh_pair_records", "toss_pair_faces", "toss_grid_upload", "toss_gravity_eval", "toss_compute_motion",
     "toss_rotate_points", "toss_workspace_layout", "toss_propagate", "toss_integrate", "toss_collision_verdict", "toss_num_samples", "toss_resample", "toss_dense_eval",
     "toss_fitness_eval", "toss_update_tensor", "toss_is_outside", "toss_population_fitness",
     "toss_population_fitness_host", "toss_measure_fp64_peak", "toss_launch_count", "toss_math_probe",
@@ -125,6 +125,7 @@ def lib():
     L.toss_deal_rows.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, up]
     L.toss_pack_result.argtypes = [vp, vp, vp, i32, i32, vp, up]
     L.toss_unpack_result.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, up]
+    L.toss_mesh_pair_records.argtypes = [vp, c_double_p]
     L.toss_gaco_sample.argtypes = [vp, c_double_p, i32, i32, c_double_p, c_double_p, c_double_p, c_double_p,
                                    C.c_uint64, C.c_uint64, i32, i32, vp, up]
     L.toss_measure_fp64_peak.argtypes = [vp, c_double_p]
@@ -238,6 +239,13 @@ class Context:
         out = np.empty((n, 3), np.int32)
         _check(lib().toss_mesh_pairs(self.h, out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
+
+    def mesh_pair_records(self):
+        """The per-pair constants the device built at upload: float64 [n][43] (include/toss_b200.h)."""
+        n = lib().toss_mesh_num_pairs(self.h)
+        out = np.empty((n, 44))
+        _check(lib().toss_mesh_pair_records(self.h, _dp(out)))
+        return out[:, :43].copy()
 
     def upload_grid(self, r, theta, phi, bool_tensor):
         r, theta, phi = _f64(r), _f64(theta), _f64(phi)

@@ -79,6 +79,14 @@ int toss_mesh_pairs(const toss_ctx *ctx, int32_t *out)
     memcpy(out, ctx->h_pairs, sizeof(int32_t) * 3 * (size_t)ctx->n_pairs);
     return 0;
 }
+int toss_mesh_pair_records(toss_ctx *ctx, double *h_out)
+{
+    TOSS_REQUIRE(ctx && h_out && ctx->d_pair_aos, "toss_mesh_pair_records: no mesh uploaded");
+    TOSS_ENTER(ctx);
+    TOSS_CHECK_CUDA(cudaMemcpy(h_out, ctx->d_pair_aos, sizeof(double) * kPairAosStride * (size_t)ctx->n_pairs,
+                               cudaMemcpyDeviceToHost));
+    return 0;
+}
 // the matching alone (host integer work, no device): out = int32[3 * F] capacity, returns the number of records
 int toss_pair_faces(const int32_t *h_faces, int F, int V, int32_t *out)
 {
@@ -101,19 +109,28 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
     TOSS_ENTER(ctx);
     for (int i = 0; i < 3 * F; ++i)
         TOSS_REQUIRE(h_faces[i] >= 0 && h_faces[i] < V, "toss_mesh_upload: face index out of range");
-    // the pairing and the per-pair constants (pairs.cu)
+    // the pairing (host, integer work).  The sum runs over faces that share edges: the surface must be closed and
+    // consistently oriented -- every edge used by exactly two faces, in opposite directions (polyhedral_gravity
+    // requires the same of its input and silently returns garbage otherwise).
     std::vector<int32_t> pairs;
-    toss_build_face_pairs(h_faces, F, V, pairs);
+    int n_unmatched = 0, first_unmatched = 0;
+    toss_build_face_pairs(h_faces, F, V, pairs, &n_unmatched, &first_unmatched);
+    TOSS_REQUIRE(n_unmatched == 0,
+                 "toss_mesh_upload: the mesh is not a closed, consistently oriented surface: " +
+                     std::to_string(n_unmatched) + " face edge(s) without an opposite partner (first: face " +
+                     std::to_string(first_unmatched / 3) + ", edge " + std::to_string(first_unmatched % 3) + ")");
     const int n_pairs = (int)(pairs.size() / 3);
-    std::vector<double> rec((size_t)n_pairs * kPairFields);
-    for (int i = 0; i < n_pairs; ++i)
-        TOSS_REQUIRE(toss_pair_record(h_verts, h_faces, pairs[3 * i], pairs[3 * i + 1], pairs[3 * i + 2],
-                                      &rec[(size_t)i * kPairFields]),
-                     "toss_mesh_upload: degenerate (zero-area) face");
-    auto pair_or_pad = [&](int i, double *out) {
-        if (i < n_pairs) memcpy(out, &rec[(size_t)i * kPairFields], sizeof(double) * kPairFields);
-        else toss_pair_pad_record(out);
-    };
+    {   // outward orientation: positive volume (divergence theorem)
+        double vol6 = 0.0;
+        for (int f = 0; f < F; ++f) {
+            const double *a = h_verts + 3 * (size_t)h_faces[3 * f], *b = h_verts + 3 * (size_t)h_faces[3 * f + 1],
+                         *d = h_verts + 3 * (size_t)h_faces[3 * f + 2];
+            vol6 += a[0] * (b[1] * d[2] - b[2] * d[1]) + a[1] * (b[2] * d[0] - b[0] * d[2]) +
+                    a[2] * (b[0] * d[1] - b[1] * d[0]);
+        }
+        TOSS_REQUIRE(vol6 > 0.0, "toss_mesh_upload: the faces are wound clockwise seen from outside (negative volume): "
+                                 "flip the vertex order of every face");
+    }
     free_mesh(ctx);
     ctx->V = V;
     ctx->F = F;
@@ -175,6 +192,67 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
             for (int m = 0; m < ctx->n_mascons; ++m) mc[4 * m + 3] = ctx->GM / ctx->n_mascons;
             const double cell = ((hi[0] - lo[0]) + (hi[1] - lo[1]) + (hi[2] - lo[2])) / (3.0 * G);
             ctx->mascon_soft2 = 0.25 * cell * cell;
+            // The proxy's idea of "inside the body" (it retires a trajectory there when the real run would retire it at
+            // its first event point inside the mesh, so that the predicted cost of a collider is short like its real
+            // one): occupancy of a kProxyOcc^3 grid over the bounding box -- a cell is inside when its centre is.  One
+            // vertical line per (i, j) column: the z of its crossings with the faces, sorted; a centre is inside when an
+            // odd number of crossings lies above it.  Appended to the mascon table: lo[3] | cells per metre[3] | bits.
+            const int Q = kProxyOcc;
+            std::vector<uint64_t> bits((size_t)Q * Q * Q / 64, 0ull);
+            std::vector<double> zs;
+            for (int i = 0; i < Q; ++i)
+                for (int j = 0; j < Q; ++j) {
+                    const double ox = lo[0] + (i + 0.5) * (hi[0] - lo[0]) / Q, oy = lo[1] + (j + 0.5) * (hi[1] - lo[1]) / Q;
+                    zs.clear();
+                    for (int f = 0; f < F; ++f) {
+                        const double *a = h_verts + 3 * (size_t)h_faces[3 * f], *b = h_verts + 3 * (size_t)h_faces[3 * f + 1],
+                                     *d = h_verts + 3 * (size_t)h_faces[3 * f + 2];
+                        const double e1x = b[0] - a[0], e1y = b[1] - a[1], e2x = d[0] - a[0], e2y = d[1] - a[1];
+                        const double det = e1x * e2y - e1y * e2x;
+                        if (det == 0.0) continue;
+                        const double sx = ox - a[0], sy = oy - a[1];
+                        const double u = (sx * e2y - sy * e2x) / det, w = (e1x * sy - e1y * sx) / det;
+                        if (u < 0.0 || w < 0.0 || u + w > 1.0) continue;
+                        zs.push_back(a[2] + u * (b[2] - a[2]) + w * (d[2] - a[2]));
+                    }
+                    for (int k = 0; k < Q; ++k) {
+                        const double oz = lo[2] + (k + 0.5) * (hi[2] - lo[2]) / Q;
+                        int above = 0;
+                        for (double z : zs) above += z > oz;
+                        if (above & 1) {
+                            const int c = (i * Q + j) * Q + k;
+                            bits[c >> 6] |= 1ull << (c & 63);
+                        }
+                    }
+                }
+            {   // Erode by one cell: only cells whose 26 neighbours are inside too count.  A trajectory that merely passes
+                // close must NOT be predicted short -- it would start last and run longest; a collider missed here only
+                // keeps its long prediction and retires early, which costs nothing.
+                std::vector<uint64_t> core(bits.size(), 0ull);
+                auto in = [&](int i, int j, int k) {
+                    if (i < 0 || j < 0 || k < 0 || i >= Q || j >= Q || k >= Q) return false;
+                    const int c = (i * Q + j) * Q + k;
+                    return ((bits[c >> 6] >> (c & 63)) & 1ull) != 0;
+                };
+                for (int i = 0; i < Q; ++i)
+                    for (int j = 0; j < Q; ++j)
+                        for (int k = 0; k < Q; ++k) {
+                            bool all = true;
+                            for (int d = 0; d < 27 && all; ++d) all = in(i + d / 9 - 1, j + (d / 3) % 3 - 1, k + d % 3 - 1);
+                            if (all) {
+                                const int c = (i * Q + j) * Q + k;
+                                core[c >> 6] |= 1ull << (c & 63);
+                            }
+                        }
+                bits.swap(core);
+            }
+            for (int k = 0; k < 3; ++k) mc.push_back(lo[k]);
+            for (int k = 0; k < 3; ++k) mc.push_back(hi[k] > lo[k] ? Q / (hi[k] - lo[k]) : 0.0);
+            for (uint64_t wbits : bits) {
+                double dv;
+                memcpy(&dv, &wbits, 8);
+                mc.push_back(dv);
+            }
             TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_mascons, mc.size() * 8));
             TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_mascons, mc.data(), mc.size() * 8, cudaMemcpyHostToDevice));
         }
@@ -187,40 +265,18 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
     ctx->h_pairs = (int32_t *)malloc(sizeof(int32_t) * pairs.size());
     memcpy(ctx->h_pairs, pairs.data(), sizeof(int32_t) * pairs.size());
 
-    // (1) AoS, 44 doubles per pair, padded to whole 32-pair tiles          -> K1a thread-per-point
-    std::vector<double> aos((size_t)ctx->n_pair_aos_tiles * kPairAosTile * kPairAosStride, 0.0);
-    for (int i = 0; i < ctx->n_pair_aos_tiles * kPairAosTile; ++i) pair_or_pad(i, &aos[(size_t)i * kPairAosStride]);
-    // (2) flat slot table [22][Ppad32] double2 (slot j = fields 2j, 2j+1)  -> resident stepper, K1b
-    std::vector<double> soa((size_t)2 * kPairSlots * ctx->Ppad32, 0.0);
-    for (int i = 0; i < ctx->Ppad32; ++i) {
-        double tmp[kPairFields];
-        pair_or_pad(i, tmp);
-        for (int k = 0; k < kPairFields; ++k) soa[((size_t)(k >> 1) * ctx->Ppad32 + i) * 2 + (k & 1)] = tmp[k];
+    // every device table (three encodings of the pair records + the ray caster's face table) is built ON the device
+    // from the vertex / face / pair index arrays (pairs.cu: pair_tables_kernel, ray_table_kernel)
+    int bad_face = -1;
+    const int rc = launch_mesh_tables(ctx, h_verts, V, h_faces, F, pairs.data(), n_pairs, &bad_face);
+    if (rc < 0) {
+        free_mesh(ctx);
+        return -1;
     }
-    // (3) tiled slot table [n_tiles][22][128] double2 -> streaming stepper.  Pair i sits in tile i/128, slot row
-    //     position i%128, so lane l still owns pairs l, l+32, l+64, ... in increasing order: the same summation
-    //     order as the flat layout.
-    std::vector<double> tiles((size_t)ctx->n_pair_tiles * kPairTileDoubles, 0.0);
-    for (int t = 0; t < ctx->n_pair_tiles; ++t)
-        for (int j = 0; j < kPairTile; ++j) {
-            double tmp[kPairFields];
-            pair_or_pad(t * kPairTile + j, tmp);
-            for (int k = 0; k < kPairFields; ++k)
-                tiles[(((size_t)t * kPairSlots + (k >> 1)) * kPairTile + j) * 2 + (k & 1)] = tmp[k];
-        }
-    // (4) the faces themselves, original vertex order, [9][Fpad32]        -> ray casting (K5, event points)
-    std::vector<double> ray((size_t)kRayFields * ctx->Fpad32);
-    for (int f = 0; f < ctx->Fpad32; ++f)
-        for (int k = 0; k < kRayFields; ++k)
-            ray[(size_t)k * ctx->Fpad32 + f] = f < F ? h_verts[3 * (size_t)h_faces[3 * f + k / 3] + k % 3] : kPadVertex;
-    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_pair_aos, aos.size() * 8));
-    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_pair_soa, soa.size() * 8));
-    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_pair_tiles, tiles.size() * 8));
-    TOSS_CHECK_CUDA(cudaMalloc(&ctx->d_ray_soa, ray.size() * 8));
-    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_pair_aos, aos.data(), aos.size() * 8, cudaMemcpyHostToDevice));
-    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_pair_soa, soa.data(), soa.size() * 8, cudaMemcpyHostToDevice));
-    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_pair_tiles, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice));
-    TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_ray_soa, ray.data(), ray.size() * 8, cudaMemcpyHostToDevice));
+    if (rc > 0) {
+        free_mesh(ctx);
+        TOSS_REQUIRE(false, "toss_mesh_upload: degenerate (zero-area) face " + std::to_string(bad_face));
+    }
     return 0;
 }
 

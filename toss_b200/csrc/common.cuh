@@ -49,6 +49,8 @@ struct PairCols {
     }
 };
 constexpr int kRayFields = 9;
+constexpr int kProxyOcc = 16;           // the proxy's occupancy grid of the body: kProxyOcc^3 cells over the bounding box
+constexpr int kProxyTail = 6 + kProxyOcc * kProxyOcc * kProxyOcc / 64;   // doubles after the mascons: lo | cells/m | bits
 constexpr double kPadVertex = 1.0e9;    // padding faces sit here with N = n = |G| = 2A = 0 -> contribute exactly 0
 constexpr double kGravConst = 6.67430e-11;   // CODATA-2018, as polyhedral_gravity >= 2
 
@@ -201,9 +203,10 @@ inline UnitAxis unit_axis_host(const double a[3])
 
 // ---- face pairing (pairs.cu) -------------------------------------------------------------------------
 #include <vector>
-void toss_build_face_pairs(const int32_t *faces, int F, int V, std::vector<int32_t> &out);
-bool toss_pair_record(const double *verts, const int32_t *faces, int fA, int qA, int fB, double *rec43);
-void toss_pair_pad_record(double *rec43);
+void toss_build_face_pairs(const int32_t *faces, int F, int V, std::vector<int32_t> &out, int *n_unmatched = nullptr,
+                           int *first_unmatched = nullptr);
+int launch_mesh_tables(toss_ctx *ctx, const double *h_verts, int V, const int32_t *h_faces, int F, const int32_t *h_pairs,
+                       int n_pairs, int *bad_face);
 
 // ---- kernels' host launchers (defined in the .cu files) -------------------------------------------
 int launch_gravity(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc, double *d_pot, cudaStream_t st);

@@ -18,7 +18,7 @@
 // first (FIFO), otherwise the lowest-numbered free face takes its free neighbour of smallest (degree, edge slot).
 // Output, ascending in the first face: (fA, qA, fB) with fA < fB, qA = A's edge slot of the shared edge;
 // fB = -1 for a face left without a partner.
-void toss_build_face_pairs(const int32_t *faces, int F, int V, std::vector<int32_t> &out)
+void toss_build_face_pairs(const int32_t *faces, int F, int V, std::vector<int32_t> &out, int *n_unmatched, int *first_unmatched)
 {
     // edge table: for every directed half-edge (u -> v) of face f slot q, key = min*V + max; bucket by counting sort
     std::vector<int64_t> key((size_t)3 * F);
@@ -63,6 +63,11 @@ void toss_build_face_pairs(const int32_t *faces, int F, int V, std::vector<int32
             }
         }
         i = j;
+    }
+    if (n_unmatched) {   // a closed, consistently oriented surface has none (toss_mesh_upload refuses anything else)
+        *n_unmatched = 0;
+        for (int h = 0; h < 3 * F; ++h)
+            if (nb[h] < 0 && (*n_unmatched)++ == 0 && first_unmatched) *first_unmatched = h;
     }
     std::vector<int32_t> mate((size_t)F, -1), deg((size_t)F, 0);
     for (int f = 0; f < F; ++f)
@@ -122,8 +127,9 @@ namespace {
 struct FaceConsts {
     double N[3], n[3][3], len[3], twoA;
 };
-// N = G0 x G1 / |.|, n_q = G_q x N / |.|, |G_q|, 2A = |G0 x G1|, G_q = w_{q+1} - w_q
-bool face_consts(const double *w0, const double *w1, const double *w2, FaceConsts &o)
+// N = G0 x G1 / |.|, n_q = G_q x N / |.|, |G_q|, 2A = |G0 x G1|, G_q = w_{q+1} - w_q.  Plain IEEE + - * / sqrt in a
+// fixed order (the file is compiled -fmad=false): a second implementation of the same sequence gives the same bits.
+__device__ bool face_consts(const double *w0, const double *w1, const double *w2, FaceConsts &o)
 {
     const double *w[3] = {w0, w1, w2};
     double G[3][3];
@@ -144,18 +150,17 @@ bool face_consts(const double *w0, const double *w1, const double *w2, FaceConst
     o.twoA = nn;
     return true;
 }
-}   // namespace
 
 // One pair record (common.cuh layout).  A = (v0, v1, v2) is face fA rotated so that the shared edge comes
 // first; B = (v1, v0, v3) is face fB in its own orientation.  A face without a partner gets a null B
 // (v3 = v2, all of B's constants zero: S_B = 0 exactly).
-bool toss_pair_record(const double *verts, const int32_t *faces, int fA, int qA, int fB, double *r)
+__device__ bool pair_record(const double *verts, const int32_t *faces, int fA, int qA, int fB, double *r)
 {
     const int i0 = faces[3 * fA + qA], i1 = faces[3 * fA + (qA + 1) % 3], i2 = faces[3 * fA + (qA + 2) % 3];
     int i3 = i2;
     if (fB >= 0) {
         int qb = 0;
-        while (!(faces[3 * fB + qb] == i1 && faces[3 * fB + (qb + 1) % 3] == i0)) ++qb;
+        while (qb < 2 && !(faces[3 * fB + qb] == i1 && faces[3 * fB + (qb + 1) % 3] == i0)) ++qb;
         i3 = faces[3 * fB + (qb + 2) % 3];
     }
     const double *v0 = verts + 3 * (size_t)i0, *v1 = verts + 3 * (size_t)i1, *v2 = verts + 3 * (size_t)i2,
@@ -191,8 +196,101 @@ bool toss_pair_record(const double *verts, const int32_t *faces, int fA, int qA,
     return true;
 }
 
-void toss_pair_pad_record(double *r)
+// Thread i builds the record of pair i (a padding record beyond n_pairs: every vertex at kPadVertex, every constant 0)
+// and writes it into the three encodings of DESIGN.md section 4:
+//   aos   [n_aos_slots][44]                  K1a, LDS.128 broadcast reads
+//   soa   [22][Ppad32] double2               K1b, resident stepper
+//   tiles [n_tiles][22][kPairTile] double2   streaming stepper (pair i -> tile i / kPairTile, position i % kPairTile)
+// A zero-area face raises *degenerate (the upload then fails).
+__global__ void __launch_bounds__(128) pair_tables_kernel(const double *__restrict__ verts, const int32_t *__restrict__ faces,
+                                                          const int32_t *__restrict__ pairs, int n_pairs, int n_aos_slots,
+                                                          int Ppad32, int n_tile_slots, double *__restrict__ aos,
+                                                          double *__restrict__ soa, double *__restrict__ tiles,
+                                                          int *__restrict__ degenerate)
 {
-    for (int k = 0; k < kPairFields; ++k) r[k] = 0.0;
-    for (int k = 0; k < 12; ++k) r[k] = kPadVertex;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_aos_slots && i >= Ppad32 && i >= n_tile_slots) return;
+    double r[kPairFields];
+    bool ok = true;
+    if (i < n_pairs) ok = pair_record(verts, faces, pairs[3 * i], pairs[3 * i + 1], pairs[3 * i + 2], r);
+    if (i >= n_pairs || !ok) {
+        for (int k = 0; k < kPairFields; ++k) r[k] = k < 12 ? kPadVertex : 0.0;
+        if (!ok) atomicExch(degenerate, 1 + pairs[3 * i]);
+    }
+    if (i < n_aos_slots) {
+        for (int k = 0; k < kPairFields; ++k) aos[(size_t)i * kPairAosStride + k] = r[k];
+        aos[(size_t)i * kPairAosStride + kPairFields] = 0.0;
+    }
+    if (i < Ppad32) {
+        for (int k = 0; k < 2 * kPairSlots; ++k)
+            soa[((size_t)(k >> 1) * Ppad32 + i) * 2 + (k & 1)] = k < kPairFields ? r[k] : 0.0;
+    }
+    if (i < n_tile_slots) {
+        const int t = i / kPairTile, j = i % kPairTile;
+        for (int k = 0; k < 2 * kPairSlots; ++k)
+            tiles[(((size_t)t * kPairSlots + (k >> 1)) * kPairTile + j) * 2 + (k & 1)] = k < kPairFields ? r[k] : 0.0;
+    }
+}
+
+// the faces themselves, original vertex order, [9][Fpad32] -> ray casting (K5, event points)
+__global__ void __launch_bounds__(128) ray_table_kernel(const double *__restrict__ verts, const int32_t *__restrict__ faces,
+                                                        int F, int Fpad32, double *__restrict__ ray)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Fpad32) return;
+    for (int k = 0; k < kRayFields; ++k)
+        ray[(size_t)k * Fpad32 + f] = f < F ? verts[3 * (size_t)faces[3 * f + k / 3] + k % 3] : kPadVertex;
+}
+}   // namespace
+
+// Builds every device table of the mesh from (verts, faces, pairs) ON the device: the host only matches the faces
+// (integer work) and copies the three index / coordinate arrays up.  Returns 0, or 1 + face index of a zero-area face.
+int launch_mesh_tables(toss_ctx *ctx, const double *h_verts, int V, const int32_t *h_faces, int F, const int32_t *h_pairs,
+                       int n_pairs, int *bad_face)
+{
+    *bad_face = -1;
+    const int n_aos_slots = ctx->n_pair_aos_tiles * kPairAosTile, n_tile_slots = ctx->n_pair_tiles * kPairTile;
+    double *d_verts = nullptr;
+    int32_t *d_faces = nullptr, *d_pairs = nullptr;
+    int *d_flag = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_verts);
+        cudaFree(d_faces);
+        cudaFree(d_pairs);
+        cudaFree(d_flag);
+    };
+#define MT_CHECK(call)                                        \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) {                              \
+            toss_set_error(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+            cleanup();                                        \
+            return -1;                                        \
+        }                                                     \
+    } while (0)
+    MT_CHECK(cudaMalloc(&d_verts, sizeof(double) * 3 * (size_t)V));
+    MT_CHECK(cudaMalloc(&d_faces, sizeof(int32_t) * 3 * (size_t)F));
+    MT_CHECK(cudaMalloc(&d_pairs, sizeof(int32_t) * 3 * (size_t)n_pairs));
+    MT_CHECK(cudaMalloc(&d_flag, sizeof(int)));
+    MT_CHECK(cudaMemcpy(d_verts, h_verts, sizeof(double) * 3 * (size_t)V, cudaMemcpyHostToDevice));
+    MT_CHECK(cudaMemcpy(d_faces, h_faces, sizeof(int32_t) * 3 * (size_t)F, cudaMemcpyHostToDevice));
+    MT_CHECK(cudaMemcpy(d_pairs, h_pairs, sizeof(int32_t) * 3 * (size_t)n_pairs, cudaMemcpyHostToDevice));
+    MT_CHECK(cudaMemset(d_flag, 0, sizeof(int)));
+    MT_CHECK(cudaMalloc(&ctx->d_pair_aos, sizeof(double) * (size_t)n_aos_slots * kPairAosStride));
+    MT_CHECK(cudaMalloc(&ctx->d_pair_soa, sizeof(double) * 2 * kPairSlots * (size_t)ctx->Ppad32));
+    MT_CHECK(cudaMalloc(&ctx->d_pair_tiles, sizeof(double) * (size_t)ctx->n_pair_tiles * kPairTileDoubles));
+    MT_CHECK(cudaMalloc(&ctx->d_ray_soa, sizeof(double) * kRayFields * (size_t)ctx->Fpad32));
+    int n = n_aos_slots > ctx->Ppad32 ? n_aos_slots : ctx->Ppad32;
+    n = n > n_tile_slots ? n : n_tile_slots;
+    pair_tables_kernel<<<(n + 127) / 128, 128>>>(d_verts, d_faces, d_pairs, n_pairs, n_aos_slots, ctx->Ppad32, n_tile_slots,
+                                                 ctx->d_pair_aos, ctx->d_pair_soa, ctx->d_pair_tiles, d_flag);
+    ray_table_kernel<<<(ctx->Fpad32 + 127) / 128, 128>>>(d_verts, d_faces, F, ctx->Fpad32, ctx->d_ray_soa);
+    ctx->launches += 2;
+    MT_CHECK(cudaGetLastError());
+    int flag = 0;
+    MT_CHECK(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+#undef MT_CHECK
+    cleanup();
+    if (flag) *bad_face = flag - 1;
+    return flag ? 1 : 0;
 }

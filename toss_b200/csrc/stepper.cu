@@ -63,6 +63,7 @@ struct StepArgs {
     const int32_t *order;      // queue position -> trajectory index (longest predicted first), or NULL
     int first_round, first_extra;   // static first round: every CTA takes first_round queue positions, the first
                                     // first_extra CTAs one more (see the fetch)
+    int interleave;            // static round: position slot * CTAs + b instead of a contiguous block per CTA
     int proxy_n;               // PROXY instantiation: number of mascons (pair_soa then points at [n][4] x y z G*m)
     double proxy_soft2;
     int32_t *proxy_cost;       // PROXY: predicted RHS count per trajectory
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int team = wid / kTeam, rank = wid % kTeam;
-    const int mesh_doubles = kProxy ? 4 * a.proxy_n : (kStream ? kK2Stages * kPairTileDoubles : 2 * kPairSlots * a.Ppad32);
+    const int mesh_doubles = kProxy ? 4 * a.proxy_n + kProxyTail : (kStream ? kK2Stages * kPairTileDoubles : 2 * kPairSlots * a.Ppad32);
     double *mesh = reinterpret_cast<double *>(smem_raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(mesh + mesh_doubles);   // full[3] empty[3] (STREAM) / full[1]
     double *wstate = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)wid * warp_state_doubles(a.n_man);
@@ -275,9 +276,13 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
             // ring.  Later trajectories come from the atomic cursor, which starts behind the static round.
             int nxt = 0;
             const int b = (int)blockIdx.x;
+            // Few trajectories per warp (a shard of a strong-scaled population, a.interleave): the static positions
+            // are interleaved (slot * CTAs + b), so that every SM gets the same mix of lengths and none is left with
+            // sixteen of the longest trajectories -- contiguous blocks cost 10 % at 1.7 trajectories per warp.
             const int mine = a.first_round + (b < a.first_extra ? 1 : 0);   // static positions of this CTA
             if (first_fetch && team < mine) {
-                nxt = b * a.first_round + (b < a.first_extra ? b : a.first_extra) + team;
+                nxt = a.interleave ? team * (int)gridDim.x + b
+                                   : b * a.first_round + (b < a.first_extra ? b : a.first_extra) + team;
             } else {
                 if (lane == 0) nxt = atomicAdd(a.queue, 1) + (int)gridDim.x * a.first_round + a.first_extra;
                 nxt = __shfl_sync(0xffffffffu, nxt, 0);
@@ -580,7 +585,19 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
         if (stage == 0) {
             // f0 at a segment start or at a freshly accepted state: this is a knot
             if (kProxy) {
-                // no knots for the proxy run
+                // no knots for the proxy run.  An accepted state inside the body (occupancy grid appended to the mascon
+                // table) is where the real run finds its first event point inside the mesh and -- with
+                // stop_on_collision -- retires: the proxy does the same, so that a collider's predicted cost is short
+                if (after_accept && p.stop_on_collision && p.activate_event) {
+                    const double *occ = mesh + 4 * a.proxy_n;
+                    const double gx = (qx - occ[0]) * occ[3], gy = (qy - occ[1]) * occ[4], gz = (qz - occ[2]) * occ[5];
+                    if (gx >= 0.0 && gy >= 0.0 && gz >= 0.0 && gx < (double)kProxyOcc && gy < (double)kProxyOcc &&
+                        gz < (double)kProxyOcc) {
+                        const int c = ((int)gx * kProxyOcc + (int)gy) * kProxyOcc + (int)gz;
+                        const unsigned long long wbits = reinterpret_cast<const unsigned long long *>(occ + 6)[c >> 6];
+                        if ((wbits >> (c & 63)) & 1ull) collided = 1;
+                    }
+                }
             } else if (nk >= a.knot_cap) {
                 status = 3;
             } else {
@@ -852,7 +869,8 @@ static int launch_proxy(toss_ctx *ctx, const StepArgs &a, int32_t *d_cost, cudaS
     if (const char *e = getenv("TOSS_B200_PROXY_TOL")) ptol = atof(e) > 0.0 ? atof(e) : ptol;   // developer override
     if (px.p.rtol < ptol) px.p.rtol = ptol;
     if (px.p.atol < ptol) px.p.atol = ptol;
-    const size_t psmem = (size_t)4 * ctx->n_mascons * 8 + stepper_state_bytes(a.n_man);
+    const size_t psmem = ((size_t)4 * ctx->n_mascons + kProxyTail) * 8 + stepper_state_bytes(a.n_man);
+    px.interleave = 0;
     const int pctas = a.pop < K2_MINBLOCKS * ctx->sm_count ? a.pop : K2_MINBLOCKS * ctx->sm_count;
     px.first_round = a.pop / pctas < kK2Warps ? a.pop / pctas : kK2Warps;
     px.first_extra = a.pop / pctas < kK2Warps ? a.pop % pctas : 0;
@@ -954,6 +972,14 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     a.first_extra = pop / ctas < kK2Warps / team ? pop % ctas : 0;
     if (const char *e = getenv("TOSS_B200_FIRST_ROUND"))   // developer A/B: 1 = one static position per CTA
         if (atoi(e) == 1) a.first_round = 1, a.first_extra = 0;
+    // Few trajectories per warp and a longest-first queue (own proxy run, or rows pre-ordered by the multi-GPU deal):
+    // interleaved static round (see the fetch).  lp, one 4096-row shard of the 32768 population: 175 -> 159 ms.
+    // Measured and dropped: the head of the queue on CTAs that run only 4 / 8 / 12 warps (two per scheduler: 22
+    // instead of 35 us per evaluation for the longest trajectories) -- 157 .. 160 ms for 4 .. 16 such CTAs, no gain:
+    // at 1.7 trajectories per warp the tail is the bulk of two-trajectory warps, not the few longest ones.
+    const bool ordered = lpt || ctx->queue_order_mode == 1;
+    a.interleave = (ordered && (long long)pop * team < 4LL * slots) ? 1 : 0;
+    if (const char *e = getenv("TOSS_B200_INTERLEAVE")) a.interleave = atoi(e) != 0;   // developer A/B
     const size_t smem = resident ? resident_bytes : stream_bytes;
 #define TOSS_LAUNCH_STEPPER(STREAM, TEAM)                                                                          \
     do {                                                                                                           \
