@@ -511,10 +511,13 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     }
                     spar ^= 1;
                 } else if (active) {
-                    const double2 *tile = reinterpret_cast<const double2 *>(mesh + (size_t)s * kPairTileDoubles) + lane;
+                    // (a running row pointer and a down-counter: the loop carries no lane id, no tile length and no
+                    //  kernel parameter -- ptxas otherwise re-reads all three for every row to save registers, ~80
+                    //  cycles that a warp alone on its scheduler cannot hide)
+                    const double2 *rp = reinterpret_cast<const double2 *>(mesh + (size_t)s * kPairTileDoubles) + lane;
 #pragma unroll kK2Unroll
-                    for (int f = 0; f < f_end; f += 32) {
-                        const PairCols<false> cols{tile + f, kPairTile};
+                    for (int r = f_end >> 5; r > 0; --r, rp += 32) {
+                        const PairCols<false> cols{rp, kPairTile};
                         pair_term<false, kCompactRows>(cols, Px, Py, Pz, ax, ay, az, pv, scr);
                     }
                 }
@@ -555,9 +558,10 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
                     spar ^= 1;
                 }
             } else {
+                const double2 *rp = reinterpret_cast<const double2 *>(mesh) + lane;   // (as in the streaming loop)
 #pragma unroll kK2Unroll
-                for (int f = lane; f < Fp; f += 32) {
-                    const PairCols<false> cols{reinterpret_cast<const double2 *>(mesh) + f, Fp};
+                for (int r = Fp >> 5; r > 0; --r, rp += 32) {
+                    const PairCols<false> cols{rp, Fp};
                     pair_term<false, kCompactRows>(cols, Px, Py, Pz, ax, ay, az, pv, scr);
                 }
             }
