@@ -5,12 +5,13 @@ cd "$(dirname "$0")/../toss_b200/csrc"
 mkdir -p ../../build/variants
 build() { # name flags...
   name=$1; shift
-  nvcc -O3 -std=c++17 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr "$@" -shared -o ../../build/variants/libtoss_$name.so api.cu pairs.cu gravity_kernels.cu stepper.cu fitness.cu sharding.cu -lcudart 2> ../../build/variants/$name.log
+  nvcc -O3 -std=c++17 -lineinfo -fmad=false -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr "$@" -shared -o ../../build/variants/libtoss_$name.so api.cu pairs.cu gravity_kernels.cu stepper.cu fitness.cu sharding.cu gaco.cu -lcudart 2> ../../build/variants/$name.log
   grep -A2 "stepper_kernelILb1ELi1ELb0ELb0" ../../build/variants/$name.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name"
 }
 for v in "$@"; do
   case $v in
     base)   build base ;;
+    unroll2) build unroll2 -DK2_UNROLL=2 ;;
     st4)    build st4 -DK2_STAGES=4 ;;
     t64s6)  build t64s6 -DPAIR_TILE=64 -DK2_STAGES=6 ;;
     t64s8)  build t64s8 -DPAIR_TILE=64 -DK2_STAGES=8 ;;
