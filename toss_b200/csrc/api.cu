@@ -257,6 +257,13 @@ int toss_mesh_upload(toss_ctx *ctx, const double *h_verts, int V, const int32_t 
             TOSS_CHECK_CUDA(cudaMemcpy(ctx->d_mascons, mc.data(), mc.size() * 8, cudaMemcpyHostToDevice));
         }
     }
+    ctx->max_edge = 0.0;
+    for (int f = 0; f < F; ++f)
+        for (int q = 0; q < 3; ++q) {
+            const double *a = h_verts + 3 * (size_t)h_faces[3 * f + q], *b = h_verts + 3 * (size_t)h_faces[3 * f + (q + 1) % 3];
+            const double e = sqrt((b[0] - a[0]) * (b[0] - a[0]) + (b[1] - a[1]) * (b[1] - a[1]) + (b[2] - a[2]) * (b[2] - a[2]));
+            if (e > ctx->max_edge) ctx->max_edge = e;
+        }
     ctx->Fpad32 = (F + 31) / 32 * 32;
     ctx->n_pairs = n_pairs;
     ctx->Ppad32 = (n_pairs + 31) / 32 * 32;

@@ -51,6 +51,7 @@ struct PairCols {
 constexpr int kRayFields = 9;
 constexpr int kProxyOcc = 16;           // the proxy's occupancy grid of the body: kProxyOcc^3 cells over the bounding box
 constexpr int kProxyTail = 6 + kProxyOcc * kProxyOcc * kProxyOcc / 64;   // doubles after the mascons: lo | cells/m | bits
+constexpr double kLaneFarEdge = 400.0;   // K1a decides the far tier per lane on meshes whose longest edge is shorter [m]
 constexpr double kPadVertex = 1.0e9;    // padding faces sit here with N = n = |G| = 2A = 0 -> contribute exactly 0
 constexpr double kGravConst = 6.67430e-11;   // CODATA-2018, as polyhedral_gravity >= 2
 
@@ -66,6 +67,7 @@ struct toss_ctx {
     double *d_mascons = nullptr;                 // [n_mascons][4] x y z G*m: proxy field of the work-queue cost predictor
     int n_mascons = 0;
     double mascon_soft2 = 0.0;
+    double max_edge = 0.0;                       // longest edge of the mesh [m] (chooses the thread-per-point kernel's tier rule)
     int n_pairs = 0;                 // pair records (matched pairs + faces left single)
     int Ppad32 = 0;                  // n_pairs rounded up to 32 (flat SoA)
     int n_pair_aos_tiles = 0;        // ceil(n_pairs / 32)

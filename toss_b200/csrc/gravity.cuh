@@ -24,12 +24,13 @@
 // multiply N_A and N_B.  Shared between the two: the distances to v0 and v1, r0.r1, l0*l1 and the edge term
 // LN_0 of e0; on the common path ONE division serves the five edge quotients and the two solid-angle quotients.
 // kMode says how the caller's warp is organised:
-//   kPairLane     every lane has its own field point (thread-per-point kernel): no warp votes;
+//   kPairLane     every lane has its own field point (thread-per-point kernel): no warp votes, 7 / 5 coefficients;
+//   kPairLaneFar  the same with the far tier decided PER LANE (fine meshes: lanes rarely disagree);
 //   kPairRow      the warp is converged on the call and its 32 lanes hold one ROW of 32 consecutive pair records for
 //                 ONE field point: the row's tier (far / not) is decided by a vote;
 //   kPairRowSmem  the same, plus `scratch` = 96 doubles of shared memory owned by the warp: the out-of-range edge
 //                 terms of the row are compacted across the lanes (below).
-enum : int { kPairLane = 0, kPairRow = 1, kPairRowSmem = 2 };
+enum : int { kPairLane = 0, kPairRow = 1, kPairRowSmem = 2, kPairLaneFar = 3 };
 
 // Everything of a pair term that does not depend on the tier: distances, plane / edge heights, the seven quotients
 // (ONE division), their squares and the high words the range tests look at.  (A caller that only needs some of the
@@ -133,6 +134,7 @@ template <int kMode>
 __device__ __forceinline__ void pair_tail_general(const PairFront &F, double &SA, double &SB, double *scratch)
 {
     constexpr bool kCompact = kMode == kPairRowSmem;
+    constexpr bool kLane = kMode == kPairLane || kMode == kPairLaneFar;
     constexpr unsigned kFull = 0xffffffffu;
     const double z0 = F.z0, z1 = F.z1, z2 = F.z2, z3 = F.z3, z4 = F.z4;
     const double z0s = F.z0s, z1s = F.z1s, z2s = F.z2s, z3s = F.z3s, z4s = F.z4s;
@@ -145,7 +147,7 @@ __device__ __forceinline__ void pair_tail_general(const PairFront &F, double &SA
     // the lane-per-pair kernels take an 11-coefficient atanh up to z^2 < 0.16 (a third as many
     // rows with out-of-range edge terms as with the 7-coefficient one up to 0.04; the extra 20 FP64 instructions fall
     // on the 5 % of the rows that get here); the thread-per-point kernel keeps 7 coefficients up to 0.04
-    constexpr int kZ2Max = kMode == kPairLane ? kHiZ2Max : kHiZ2Wide;
+    constexpr int kZ2Max = kLane ? kHiZ2Max : kHiZ2Wide;
     const bool anybad = (hzmax >= kZ2Max) | (hqmax >= kHiQ2Max) | (hdmin <= 0);
     // the warp vote is issued BEFORE the polynomials so that its latency (integer maxima -> compare -> vote) hides
     // behind them instead of sitting at the end of the row with nothing left to issue
@@ -153,7 +155,7 @@ __device__ __forceinline__ void pair_tail_general(const PairFront &F, double &SA
     // HALF values from here on: atanh(z) and atan(q) instead of 2 atanh(z) = LN and 2 atan(q) = omega.  Scaling by
     // 2 is exact, so S/2 and the accumulated sum/2 carry the same bits; the callers multiply by 2 G rho at the end.
     double ln0, ln1, ln2, ln3, ln4;
-    if (kMode == kPairLane) {
+    if (kLane) {
         ln0 = tm_atanh_mm(z0, z0s), ln1 = tm_atanh_mm(z1, z1s), ln2 = tm_atanh_mm(z2, z2s), ln3 = tm_atanh_mm(z3, z3s),
         ln4 = tm_atanh_mm(z4, z4s);
     } else {
@@ -230,7 +232,17 @@ __device__ __forceinline__ void pair_S(Fld fld, double Px, double Py, double Pz,
     const PairFront F = pair_front(fld, Px, Py, Pz);
     hpA_out = F.hpA;
     hpB_out = F.hpB;
-    if (kMode != kPairLane) {
+    if (kMode == kPairLaneFar) {
+        // thread-per-point kernel on a fine mesh: the far tier is the LANE's -- a function of (pair, point) alone, so a
+        // point's value does not depend on its neighbours in the batch.  Lanes that disagree diverge and the warp runs
+        // both tails: that pays when faces are small against the distances (full mesh, 1 M shell points: 136 -> 129 ms)
+        // and costs when they are not (lp: 13.9 -> 16.5 ms), so the launcher picks by the mesh's longest edge.
+        if (pair_lane_far(F)) {
+            pair_tail_far(F, SA, SB);
+            return;
+        }
+    } else if (kMode == kPairLane) {
+    } else {
         if (__all_sync(kFull, pair_lane_far(F))) {
             pair_tail_far(F, SA, SB);
             return;

@@ -21,7 +21,7 @@ constexpr int kPairTileBytes = kPairAosTile * kPairAosStride * 8;
 #endif
 constexpr int kK1Unroll = K1_UNROLL;
 
-template <bool kPot>
+template <bool kPot, int kMode = kPairLane>
 __global__ void __launch_bounds__(kK1Threads, K1_MINBLOCKS)
 gravity_points_kernel(const double *__restrict__ pair_aos, int n_tiles, int last_tile_pairs,
                            const double *__restrict__ pts, int64_t n,
@@ -74,7 +74,7 @@ gravity_points_kernel(const double *__restrict__ pair_aos, int n_tiles, int last
 #pragma unroll kK1Unroll
         for (int f = 0; f < p_end; ++f) {
             const double *rec = tile + f * kPairAosStride;
-            pair_term<kPot>([rec](int k) { return rec[k]; }, Px, Py, Pz, ax, ay, az, pv);
+            pair_term<kPot, kMode>([rec](int k) { return rec[k]; }, Px, Py, Pz, ax, ay, az, pv);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -304,17 +304,23 @@ int launch_gravity(toss_ctx *ctx, const double *d_pts, int64_t n, double *d_acc,
         const int64_t blocks = (n + kK1Threads - 1) / kK1Threads;
         TOSS_REQUIRE(blocks < 2147483647LL, "toss_gravity_eval: too many points for one launch");
         const int last = ctx->n_pairs - (ctx->n_pair_aos_tiles - 1) * kPairAosTile;   // skip the padding records
+#define TOSS_LAUNCH_K1(POT, MODE)                                                                                  \
+    do {                                                                                                           \
+        TOSS_CHECK_CUDA(cudaFuncSetAttribute(gravity_points_kernel<POT, MODE>,                                     \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        gravity_points_kernel<POT, MODE><<<(unsigned)blocks, kK1Threads, smem, st>>>(                              \
+            ctx->d_pair_aos, ctx->n_pair_aos_tiles, last, d_pts, n, d_acc, POT ? d_pot : nullptr, ctx->Grho);      \
+    } while (0)
+        // per-lane far tier when the faces are small (longest edge below kLaneFarEdge metres): see gravity.cuh
+        const bool lane_far = ctx->max_edge > 0.0 && ctx->max_edge < kLaneFarEdge;
         if (d_pot) {
-            TOSS_CHECK_CUDA(cudaFuncSetAttribute(gravity_points_kernel<true>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gravity_points_kernel<true><<<(unsigned)blocks, kK1Threads, smem, st>>>(
-                ctx->d_pair_aos, ctx->n_pair_aos_tiles, last, d_pts, n, d_acc, d_pot, ctx->Grho);
+            if (lane_far) TOSS_LAUNCH_K1(true, kPairLaneFar);
+            else TOSS_LAUNCH_K1(true, kPairLane);
         } else {
-            TOSS_CHECK_CUDA(cudaFuncSetAttribute(gravity_points_kernel<false>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gravity_points_kernel<false><<<(unsigned)blocks, kK1Threads, smem, st>>>(
-                ctx->d_pair_aos, ctx->n_pair_aos_tiles, last, d_pts, n, d_acc, nullptr, ctx->Grho);
+            if (lane_far) TOSS_LAUNCH_K1(false, kPairLaneFar);
+            else TOSS_LAUNCH_K1(false, kPairLane);
         }
+#undef TOSS_LAUNCH_K1
     }
     ctx->launches++;
     TOSS_CHECK_CUDA(cudaGetLastError());
