@@ -15,6 +15,11 @@ for v in "$@"; do
     st4)    build st4 -DK2_STAGES=4 ;;
     t64s6)  build t64s6 -DPAIR_TILE=64 -DK2_STAGES=6 ;;
     t64s8)  build t64s8 -DPAIR_TILE=64 -DK2_STAGES=8 ;;
+    w12)    build w12 -DK2_WARPS=12 ;;
+    w14)    build w14 -DK2_WARPS=14 ;;
+    w10)    build w10 -DK2_WARPS=10 ;;
+    w8)     build w8 -DK2_WARPS=8 ;;
+    w12u2)  build w12u2 -DK2_WARPS=12 -DK2_UNROLL=2 ;;
     w20)    build w20 -DK2_WARPS=20 ;;
     w24)    build w24 -DK2_WARPS=24 ;;
     hint)   build hint -DK2_WAIT_HINT=20000 ;;

@@ -39,6 +39,7 @@
 #define K2_UNROLL 1
 #endif
 constexpr int kK2Warps = K2_WARPS;
+constexpr int kK2WarpsFew = 12;            // CTA size for few trajectories per warp (divisible by the team sizes 2 and 4)
 constexpr int kK2Threads = kK2Warps * 32;
 constexpr int kK2Stages = K2_STAGES;
 constexpr int kK2Unroll = K2_UNROLL;
@@ -119,9 +120,13 @@ __device__ __forceinline__ void team_bar(int team, int nthreads)
 
 // kProxy: the same state machine integrating through a mascon proxy of the body (no mesh, no knots, no events); its
 // RHS count per trajectory is the cost key of the longest-first work queue of the real run.
-template <bool kStream, int kTeam, bool kProxy = false>
-__global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const StepArgs a)
+// kW: warps per CTA.  16 warps x 128 registers (ptxas spills ~330 bytes) or 12 warps x ~160 registers (no spills):
+// the same throughput within 2.5 % on a population that queues deep, and a warp that runs 10 % faster when there are
+// few trajectories per warp (small populations, shards of a strong-scaled one) -- the launcher picks.
+template <bool kStream, int kTeam, bool kProxy = false, int kW = kK2Warps>
+__global__ void __launch_bounds__(kW * 32, K2_MINBLOCKS) stepper_kernel(const StepArgs a)
 {
+    constexpr int kTeamBufsW = kTeamBufs ? kW / 2 : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int team = wid / kTeam, rank = wid % kTeam;
@@ -130,11 +135,11 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
     uint64_t *bars = reinterpret_cast<uint64_t *>(mesh + mesh_doubles);   // full[3] empty[3] (STREAM) / full[1]
     double *wstate = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)wid * warp_state_doubles(a.n_man);
     double *sy = wstate, *sk = wstate + 6, *meta = wstate + 84, *seg_t = wstate + 86, *sdv = seg_t + (a.n_man + 2);
-    double *tbuf = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)kK2Warps * warp_state_doubles(a.n_man) +
+    double *tbuf = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)kW * warp_state_doubles(a.n_man) +
                    (size_t)team * kTeamBufDoubles;                       // team mailbox: P, mode, S buffers
     // per-warp scratch of pair_S (compaction of the out-of-range edge terms of a row): 96 doubles
-    double *scr = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)kK2Warps * warp_state_doubles(a.n_man) +
-                  (size_t)kTeamBufs * kTeamBufDoubles + (size_t)wid * kScratchDoubles;
+    double *scr = reinterpret_cast<double *>(bars + kK2BarSlots) + (size_t)kW * warp_state_doubles(a.n_man) +
+                  (size_t)kTeamBufsW * kTeamBufDoubles + (size_t)wid * kScratchDoubles;
     volatile double *tP = tbuf;
     volatile int *tmode = reinterpret_cast<volatile int *>(tbuf + 3);
     double *sbuf = tbuf + 4;
@@ -142,12 +147,12 @@ __global__ void __launch_bounds__(kK2Threads, K2_MINBLOCKS) stepper_kernel(const
 
     int *live = reinterpret_cast<int *>(bars + 2 * kK2Stages);   // warps that have not retired yet (STREAM)
     if (tid == 0) {
-        *live = kK2Warps;
+        *live = kW;
         for (int s = 0; s < kK2Stages; ++s) live[1 + s] = -1;
         if (kStream) {
             for (int s = 0; s < kK2Stages; ++s) {
                 mbar_init(&bars[s], 1);
-                mbar_init(&bars[kK2Stages + s], kK2Warps);
+                mbar_init(&bars[kK2Stages + s], kW);
             }
         } else {
             mbar_init(&bars[0], 1);
@@ -823,10 +828,10 @@ int toss_workspace_layout_impl(int pop, int n_man, int knot_cap, toss_ws_layout 
     return 0;
 }
 
-static size_t stepper_state_bytes(int n_man)
+static size_t stepper_state_bytes(int n_man, int warps = kK2Warps)
 {
-    return (size_t)kK2Warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 + (size_t)kTeamBufs * kTeamBufDoubles * 8 +
-           (size_t)kK2Warps * kScratchDoubles * 8;
+    return (size_t)warps * warp_state_doubles(n_man) * 8 + kK2BarSlots * 8 +
+           (size_t)(kTeamBufs ? warps / 2 : 0) * kTeamBufDoubles * 8 + (size_t)warps * kScratchDoubles * 8;
 }
 
 // the part of StepArgs that does not depend on a workspace
@@ -938,7 +943,10 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     TOSS_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
     // warps per trajectory: one when every warp of the machine gets a trajectory; two or four below that, which fills
     // the SMs of small populations and shortens their longest trajectory.  Results do not depend on it.
-    const int slots = K2_MINBLOCKS * ctx->sm_count * kK2Warps;
+    // warps per CTA (see the kernel): 16 when trajectories queue deep (>= 5 per warp), else 12
+    int W = (long long)pop >= 5LL * K2_MINBLOCKS * ctx->sm_count * kK2Warps ? kK2Warps : kK2WarpsFew;
+    if (const char *e = getenv("TOSS_B200_WARPS")) W = atoi(e) == kK2WarpsFew ? kK2WarpsFew : kK2Warps;   // developer override
+    const int slots = K2_MINBLOCKS * ctx->sm_count * W;
     // Measured (lp / full mesh, pop 1024 .. 8192, longest-first queue): the best team size keeps the machine loaded
     // with one to two waves of teams -- 4 warps up to slots/2 trajectories, 2 up to slots, 1 beyond (a team of two
     // runs a trajectory 1.86x faster, not 2x, so once every warp has a trajectory of its own teams only cost).
@@ -965,15 +973,15 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     }
 
     NvtxRange nv_k2("toss:K2 stepper");
-    const size_t state_bytes = stepper_state_bytes(n_man);
+    const size_t state_bytes = stepper_state_bytes(n_man, W);
     const size_t resident_bytes = (size_t)2 * kPairSlots * ctx->Ppad32 * 8 + state_bytes;
     const size_t stream_bytes = (size_t)kK2Stages * kPairTileBytes + state_bytes;
     const bool resident = resident_bytes <= (size_t)(200 / K2_MINBLOCKS) * 1024;   // every CTA on an SM keeps its own copy
     // one CTA per SM as soon as there is a trajectory for it (the static first round spreads them over the CTAs)
     const int max_ctas = K2_MINBLOCKS * ctx->sm_count;
     const int ctas = pop < max_ctas ? pop : max_ctas;
-    a.first_round = pop / ctas < kK2Warps / team ? pop / ctas : kK2Warps / team;
-    a.first_extra = pop / ctas < kK2Warps / team ? pop % ctas : 0;
+    a.first_round = pop / ctas < W / team ? pop / ctas : W / team;
+    a.first_extra = pop / ctas < W / team ? pop % ctas : 0;
     if (const char *e = getenv("TOSS_B200_FIRST_ROUND"))   // developer A/B: 1 = one static position per CTA
         if (atoi(e) == 1) a.first_round = 1, a.first_extra = 0;
     // Few trajectories per warp and a longest-first queue (own proxy run, or rows pre-ordered by the multi-GPU deal):
@@ -985,11 +993,16 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
     a.interleave = (ordered && (long long)pop * team < 4LL * slots) ? 1 : 0;
     if (const char *e = getenv("TOSS_B200_INTERLEAVE")) a.interleave = atoi(e) != 0;   // developer A/B
     const size_t smem = resident ? resident_bytes : stream_bytes;
+#define TOSS_LAUNCH_STEPPER_W(STREAM, TEAM, WARPS)                                                                  \
+    do {                                                                                                           \
+        TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<STREAM, TEAM, false, WARPS>,                           \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        stepper_kernel<STREAM, TEAM, false, WARPS><<<ctas, WARPS * 32, smem, st>>>(a);                             \
+    } while (0)
 #define TOSS_LAUNCH_STEPPER(STREAM, TEAM)                                                                          \
     do {                                                                                                           \
-        TOSS_CHECK_CUDA(cudaFuncSetAttribute(stepper_kernel<STREAM, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem));                                                          \
-        stepper_kernel<STREAM, TEAM><<<ctas, kK2Threads, smem, st>>>(a);                                          \
+        if (W == kK2Warps) TOSS_LAUNCH_STEPPER_W(STREAM, TEAM, kK2Warps);                                          \
+        else TOSS_LAUNCH_STEPPER_W(STREAM, TEAM, kK2WarpsFew);                                                     \
     } while (0)
     if (resident) {
         if (team == 1) TOSS_LAUNCH_STEPPER(false, 1);
@@ -1000,6 +1013,7 @@ int launch_propagate(toss_ctx *ctx, const toss_params *p, const double *d_x, int
         else if (team == 2) TOSS_LAUNCH_STEPPER(true, 2);
         else TOSS_LAUNCH_STEPPER(true, 4);
     }
+#undef TOSS_LAUNCH_STEPPER_W
 #undef TOSS_LAUNCH_STEPPER
     ctx->launches++;
     TOSS_CHECK_CUDA(cudaGetLastError());
