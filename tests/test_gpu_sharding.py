@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from toss_b200 import parallel as P
-from tests.test_gpu_parity import FIXED_POS, both_params, ctx_for, random_population
+from tests.test_gpu_parity import FIXED_POS, both_params, bound_population, ctx_for, random_population
 
 pytestmark = pytest.mark.gpu
 
@@ -83,3 +83,33 @@ def test_failure_counts_ride_with_the_fitness():
     loc = c.population_fitness(p, xs, FIXED_POS, 2, 4)        # 4 knots: every trajectory runs out of capacity
     send = c.pack_result(loc["fitness"], loc["counters"], 8, 10).cpu().numpy()
     assert send[10] == 8.0 and send[11] == 0.0 and np.isnan(send[8:10]).all() and (send[:8] == 1e30).all()
+
+
+def test_the_proxy_predicts_colliders_short_and_never_a_survivor():
+    """The cost predictor retires a proxy trajectory deep inside the body when the real run would retire at its first
+    event point inside the mesh (stop_on_collision): colliders are predicted short, and -- what matters for the
+    schedule's tail -- no trajectory that survives is (the occupancy grid is eroded by one cell)."""
+    import torch
+    from toss_b200._native import COUNTERS_DTYPE
+    c, _ = ctx_for("lp")
+    n_man = 0
+    r = FIXED_POS
+    toward = -r / np.linalg.norm(r)
+    rng = np.random.default_rng(12)
+    # 24 chromosomes aimed at the body (1 m/s, +- 5 degrees), 40 from the converged-like family (long bound orbits)
+    aimed = np.stack([np.concatenate(([1.0], toward + 0.08 * rng.normal(size=3))) for _ in range(24)])
+    bound = bound_population(40, n_man, 77)
+    xs_h = np.vstack((aimed, bound))
+    xs = torch.from_numpy(xs_h).cuda()
+    p1, _ = both_params(stop_on_collision=1)
+    p0, _ = both_params(stop_on_collision=0)
+    cost1 = c.predict_cost(p1, xs, FIXED_POS, n_man).cpu().numpy()
+    cost0 = c.predict_cost(p0, xs, FIXED_POS, n_man).cpu().numpy()
+    res = c.population_fitness(p1, xs, FIXED_POS, n_man, 2048)
+    coll = res["collision"].cpu().numpy().astype(bool)
+    n_rhs = res["counters"].cpu().numpy().view(COUNTERS_DTYPE)["n_rhs"]
+    assert coll[:24].all() and not coll[24:].any()
+    assert np.array_equal(cost1[~coll], cost0[~coll])             # a survivor's prediction is untouched
+    assert (cost1[coll] < cost0[coll]).mean() > 0.8               # most colliders are caught ...
+    assert np.median(cost1[coll]) < 0.5 * np.median(cost1[~coll])  # ... and predicted short, like their real cost
+    assert np.median(n_rhs[coll]) < 0.5 * np.median(n_rhs[~coll])
